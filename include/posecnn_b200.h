@@ -1,0 +1,145 @@
+/*
+ * posecnn_b200.h — C ABI of libposecnn_b200.so (hand-written sm_100a CUDA).
+ *
+ * One entry point per native launcher of the reference (yuxng/PoseCNN @ 9f3dd7b).  The
+ * reference's launchers take raw device pointers + ints + an Eigen::GpuDevice; these take
+ * raw device pointers + ints + a cudaStream_t (passed as void*), so a TF1 OpKernel::Compute,
+ * a PyTorch extension or a ctypes caller can bind them without any framework type.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense, row-major, NHWC, float32 / int32 — exactly the reference layouts;
+ *   - the caller owns all memory, including the workspace (size from *_workspace_bytes);
+ *   - all work is enqueued on `stream`; no entry point synchronises or allocates;
+ *   - return value: 0 = success, negative = error (PCNN_E_*); pcnn_last_error() returns a
+ *     thread-local message.  Nothing ever calls exit() (the reference does, e.g.
+ *     lib/hough_voting_gpu_layer/hough_voting_gpu_op.cu.cc:679-684).
+ *
+ * Citations are relative to /root/reference/lib.
+ */
+#ifndef POSECNN_B200_H_
+#define POSECNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCNN_OK 0
+#define PCNN_E_INVALID (-1)   /* bad argument (rank/shape/attr), like OP_REQUIRES -> InvalidArgument */
+#define PCNN_E_WORKSPACE (-2) /* workspace too small */
+#define PCNN_E_CUDA (-3)      /* CUDA runtime error at launch */
+
+#define PCNN_MAX_ROI 128                       /* hough_voting_gpu_op.cu.cc:14 */
+#define PCNN_HOUGH_MAX_ROWS (PCNN_MAX_ROI * 9) /* hough_voting_gpu_op.cc:94 */
+
+const char* pcnn_last_error(void);
+int pcnn_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Houghvotinggpu — replaces HoughvotinggpuOp<GpuDevice>::Compute + HoughVotingLaucher
+ * (hough_voting_gpu_layer/hough_voting_gpu_op.cc:299-435, hough_voting_gpu_op.cu.cc:615-797;
+ * registration hough_voting_gpu_op.cc:37-52).  Whole batch per call, no host round trips.
+ *
+ *   label   [B,H,W] int32          vertex [B,H,W,3C] f32        extents [C,3] f32
+ *   meta    [B,num_meta] f32       gt [num_gt,13] f32 (may be NULL when num_gt == 0)
+ * Outputs are CAPACITY buffers of PCNN_HOUGH_MAX_ROWS rows, zero-filled by the call:
+ *   top_box [1152,7]  top_pose [1152,7]  top_target [1152,4C]  top_weight [1152,4C]
+ *   top_domain [1152] int32   num_rois [1] int32 = number of valid rows (the op reports
+ *   max(1, num_rois) rows, hough_voting_gpu_op.cc:379-383; the Python layer applies that rule).
+ * Hard-coded reference constants are explicit parameters with the same defaults:
+ *   inlier_threshold 0.9, label_threshold 500 (hough_voting_gpu_op.cc:356-357).
+ * Canonical order (the reference is non-deterministic): per-class pixel
+ * lists in ascending pixel index; maxima in ascending (class, cell) order; rows ordered by
+ * image then maximum.
+ * status (optional, [4] int32, device): [0] bit0 = candidate list overflow (threshold mode),
+ * [1] = number of selected cells whose interval-scan vote differed from the per-cell recount.
+ */
+int pcnn_hough_vote_workspace_bytes(int B, int H, int W, int C, int skip_pixels, float threshold_vote,
+                                    size_t* bytes);
+int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, const float* extents, const float* meta,
+                        const float* gt, int B, int H, int W, int C, int num_gt, int num_meta, int is_train,
+                        float inlier_threshold, int label_threshold, float threshold_vote,
+                        float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
+                        float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
+                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Debug / parity helper: dense vote planes [B,C,H,W] f32 (0 for classes that did not vote),
+ * computed by the same interval-scan kernels.  Used by tests to compare with the oracle. */
+int pcnn_hough_vote_planes(const int32_t* label, const float* vertex, const float* extents, const float* meta,
+                           int B, int H, int W, int C, int num_meta, float inlier_threshold,
+                           int label_threshold, int skip_pixels, float* votes, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* HoughvotinggpuGrad (hough_voting_gpu_op.cu.cc:608-612): zeros for label [B,H,W] (as f32)
+ * and vertex [B,H,W,3C]. */
+int pcnn_hough_vote_bwd(float* grad_label, float* grad_vertex, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RoiPool / RoiPoolGrad — replaces ROIPoolForwardLaucher / ROIPoolBackwardLaucher
+ * (roi_pooling_layer/roi_pooling_op_gpu.cu.cc:103-131, 232-253; registration
+ * roi_pooling_op.cc:29-50).  bottom [B,H,W,Cc]; rois [N,channel_rois] rows
+ * [b, cls, x1,y1,x2,y2,...]; top/argmax [N,ph,pw,Cc] (or 1 channel when pool_channel).
+ */
+int pcnn_roi_pool_fwd(const float* bottom, const float* rois, int num_rois, int channel_rois, int batch,
+                      int height, int width, int channels, int pooled_height, int pooled_width,
+                      float spatial_scale, int pool_channel, float* top, int32_t* argmax, void* stream);
+int pcnn_roi_pool_bwd(const float* top_diff, const int32_t* argmax, const float* rois, int batch, int num_rois,
+                      int channel_rois, int height, int width, int channels, int pooled_height,
+                      int pooled_width, float spatial_scale, int pool_channel, float* bottom_diff,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Hardlabel / HardlabelGrad — replaces HardlabelForwardLaucher / HardlabelBackwardLaucher
+ * (hard_label_layer/hard_label_op_gpu.cu.cc:32-51, 66-84; registration hard_label_op.cc:30-44).
+ * prob [B,H,W,C] f32, gt [B,H,W] int32 -> top [B,H,W,C] f32.
+ */
+int pcnn_hard_label_fwd(const float* prob, const int32_t* gt, int B, int H, int W, int C, float threshold,
+                        float* top, void* stream);
+int pcnn_hard_label_bwd(int B, int H, int W, int C, float* grad_prob, float* grad_gt, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Backproject / BackprojectGrad — replaces BackprojectForwardLaucher / BackwardLaucher
+ * (backprojecting_layer/backprojecting_op_gpu.cu.cc:128-155, 221-241; registration
+ * backprojecting_op.cc:30-53).  data [B,H,W,Cf], label [B,H,W,C], depth [B,H,W],
+ * meta [B,num_meta], label_3d [B,G,G,G,C] -> top_data [B,G,G,G,Cf], top_label [B,G,G,G,C],
+ * top_flag [B,G,G,G,Cf] (Cf channels, backprojecting_op.cc:363-369).
+ */
+int pcnn_backproject_fwd(const float* data, const float* label, const float* depth, const float* meta,
+                         const float* label_3d, int B, int H, int W, int Cf, int C, int num_meta,
+                         int grid_size, int kernel_size, float threshold, float* top_data, float* top_label,
+                         float* top_flag, void* stream);
+int pcnn_backproject_bwd(const float* top_diff, const float* depth, const float* meta, int B, int H, int W,
+                         int Cf, int num_meta, int grid_size, float* bottom_diff, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Project / ProjectGrad — replaces ProjectForwardLaucher / ProjectBackwardLaucher
+ * (projecting_layer/projecting_op_gpu.cu.cc:76-98, 172-192; registration projecting_op.cc:30-47).
+ * data [B,G,G,G,Cf], depth [B,H,W], meta [B,num_meta] -> top [B,H,W,Cf].
+ */
+int pcnn_project_fwd(const float* data, const float* depth, const float* meta, int B, int H, int W, int Cf,
+                     int num_meta, int grid_size, float* top, void* stream);
+int pcnn_project_bwd(const float* top_diff, const float* depth, const float* meta, int B, int H, int W, int Cf,
+                     int num_meta, int grid_size, int kernel_size, float threshold, float* bottom_diff,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Averagedistance / AveragedistanceGrad — replaces AveragedistanceForwardLaucher /
+ * AveragedistanceBackwardLaucher (average_distance_loss/average_distance_loss_op_gpu.cu.cc:256-343,
+ * 357-377; registration average_distance_loss_op.cc:38-54).
+ * prediction/target/weight [N,4C], point [C,P,3], symmetry [C] -> loss [1], bottom_diff [N,4C].
+ * One launch, no host synchronisation; workspace = N+64 floats (the reference allocates
+ * N*P*(54+4C+1) scratch floats and reduces through thrust + a host copy, .cu.cc:268-335).
+ */
+int pcnn_average_distance_workspace_bytes(int N, size_t* bytes);
+int pcnn_average_distance_fwd(const float* prediction, const float* target, const float* weight,
+                              const float* point, const float* symmetry, int N, int C, int P, float margin,
+                              float* loss, float* bottom_diff, void* workspace, size_t workspace_bytes,
+                              void* stream);
+int pcnn_average_distance_bwd(const float* top_diff, const float* bottom_diff, int N, int channels,
+                              float* output, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSECNN_B200_H_ */

@@ -1,0 +1,163 @@
+"""ctypes front-end of the CPU oracle (oracle/posecnn_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(posecnn_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MAX_ROWS = 128 * 9
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (seconds)."""
+    so = os.path.join(_HERE, "_build", "libposecnn_oracle.so")
+    src = os.path.join(_HERE, "posecnn_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "_build/libposecnn_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _p(a, t=ctypes.c_float):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def hough_voting_gpu(label, vertex, extents, meta, gt, is_train=0, threshold_vote=-1.0, threshold_percentage=0.02,
+                     skip_pixels=10, inlier_threshold=0.9, label_threshold=500, debug=False):
+    """Canonical-order restatement of Houghvotinggpu.  Returns the five op outputs
+    (with the >=1 dummy-row rule of hough_voting_gpu_op.cc:379-383) and, if debug,
+    a dict with the raw row count, vote planes and ambiguity counts."""
+    label = _i32(label); vertex = _f32(vertex); extents = _f32(extents); meta = _f32(meta)
+    gt = np.zeros((0, 13), np.float32) if gt is None else _f32(gt).reshape(-1, 13)
+    B, H, W = label.shape
+    C = vertex.shape[3] // 3
+    num_meta = meta.shape[-1]
+    box = np.zeros((MAX_ROWS, 7), np.float32); pose = np.zeros((MAX_ROWS, 7), np.float32)
+    target = np.zeros((MAX_ROWS, 4 * C), np.float32); weight = np.zeros((MAX_ROWS, 4 * C), np.float32)
+    domain = np.zeros((MAX_ROWS,), np.int32)
+    nrois = ctypes.c_int(0)
+    votes = np.zeros((B, C, H, W), np.float32) if debug else None
+    ambig = np.zeros((B, C, H, W), np.int32) if debug else None
+    gt_arg = gt if gt.size else np.zeros((1, 13), np.float32)
+    rc = lib().pcnn_oracle_hough(
+        _p(label, ctypes.c_int), _p(vertex), _p(extents), _p(meta), _p(gt_arg), B, H, W, C, gt.shape[0], num_meta,
+        int(is_train), ctypes.c_float(inlier_threshold), int(label_threshold), ctypes.c_float(threshold_vote),
+        ctypes.c_float(threshold_percentage), int(skip_pixels), _p(box), _p(pose), _p(target), _p(weight),
+        _p(domain, ctypes.c_int), ctypes.byref(nrois), _p(votes), _p(ambig, ctypes.c_int))
+    assert rc == 0
+    n = max(1, nrois.value)
+    outs = (box[:n].copy(), pose[:n].copy(), target[:n].copy(), weight[:n].copy(), domain[:n].copy())
+    if debug:
+        return outs, dict(num_rois=nrois.value, votes=votes, ambig=ambig)
+    return outs
+
+
+def roi_pool(data, rois, pooled_height, pooled_width, spatial_scale, pool_channel=0):
+    data = _f32(data); rois = _f32(rois)
+    B, H, W, Cc = data.shape
+    N, cr = rois.shape
+    co = 1 if pool_channel else Cc
+    top = np.zeros((N, pooled_height, pooled_width, co), np.float32)
+    arg = np.zeros((N, pooled_height, pooled_width, co), np.int32)
+    lib().pcnn_oracle_roi_pool_fwd(_p(data), _p(rois), N, cr, H, W, Cc, pooled_height, pooled_width,
+                                   ctypes.c_float(spatial_scale), int(pool_channel), _p(top), _p(arg, ctypes.c_int))
+    return top, arg
+
+
+def roi_pool_grad(data, rois, argmax, grad, pooled_height, pooled_width, spatial_scale, pool_channel=0):
+    data = _f32(data); rois = _f32(rois); argmax = _i32(argmax); grad = _f32(grad)
+    B, H, W, Cc = data.shape
+    N, cr = rois.shape
+    out = np.zeros_like(data)
+    lib().pcnn_oracle_roi_pool_bwd(_p(grad), _p(argmax, ctypes.c_int), _p(rois), B, N, cr, H, W, Cc, pooled_height,
+                                   pooled_width, ctypes.c_float(spatial_scale), int(pool_channel), _p(out))
+    return out
+
+
+def hard_label(prob, gt, threshold):
+    prob = _f32(prob); gt = _i32(gt)
+    C = prob.shape[-1]
+    top = np.empty_like(prob)
+    lib().pcnn_oracle_hard_label(_p(prob), _p(gt, ctypes.c_int), ctypes.c_long(gt.size), C,
+                                 ctypes.c_float(threshold), _p(top))
+    return top
+
+
+def project(data, depth, meta, kernel_size=0, threshold=0.0, return_ambig=False):
+    """ProjectForward: data [B,G,G,G,Cf] -> [B,H,W,Cf]."""
+    data = _f32(data); depth = _f32(depth); meta = _f32(meta)
+    B, G = data.shape[0], data.shape[1]
+    Cf = data.shape[4]
+    H, W = depth.shape[1], depth.shape[2]
+    out = np.zeros((B, H, W, Cf), np.float32)
+    amb = np.zeros((B, H, W), np.uint8)
+    lib().pcnn_oracle_pixel_gather(_p(data), _p(depth), _p(meta), B, H, W, Cf, meta.shape[-1], G, _p(out),
+                                   _p(amb, ctypes.c_ubyte))
+    return (out, amb.astype(bool)) if return_ambig else out
+
+
+def backproject_grad(top_diff, depth, meta, return_ambig=False):
+    """BackprojectBackward has ProjectForward's gather semantics on top_diff."""
+    return project(top_diff, depth, meta, return_ambig=return_ambig)
+
+
+def backproject(data, label, depth, meta, label_3d, grid_size, kernel_size, threshold, return_ambig=False):
+    data = _f32(data); label = _f32(label); depth = _f32(depth); meta = _f32(meta); label_3d = _f32(label_3d)
+    B, H, W, Cf = data.shape
+    C = label.shape[3]
+    G = grid_size
+    td = np.zeros((B, G, G, G, Cf), np.float32); tl = np.zeros((B, G, G, G, C), np.float32)
+    tf = np.zeros((B, G, G, G, Cf), np.float32); amb = np.zeros((B, G, G, G), np.uint8)
+    lib().pcnn_oracle_voxel_average(_p(data), _p(label), _p(depth), _p(meta), _p(label_3d), B, H, W, Cf, C,
+                                    meta.shape[-1], G, int(kernel_size), ctypes.c_float(threshold), _p(td), _p(tl),
+                                    _p(tf), _p(amb, ctypes.c_ubyte))
+    return (td, tl, tf, amb.astype(bool)) if return_ambig else (td, tl, tf)
+
+
+def project_grad(top_diff, depth, meta, grid_size, kernel_size, threshold, return_ambig=False):
+    """ProjectBackward: window average of top_diff [B,H,W,Cf] into [B,G,G,G,Cf]."""
+    top_diff = _f32(top_diff); depth = _f32(depth); meta = _f32(meta)
+    B, H, W, Cf = top_diff.shape
+    G = grid_size
+    out = np.zeros((B, G, G, G, Cf), np.float32); amb = np.zeros((B, G, G, G), np.uint8)
+    lib().pcnn_oracle_voxel_average(_p(top_diff), None, _p(depth), _p(meta), None, B, H, W, Cf, 0, meta.shape[-1], G,
+                                    int(kernel_size), ctypes.c_float(threshold), _p(out), None, None,
+                                    _p(amb, ctypes.c_ubyte))
+    return (out, amb.astype(bool)) if return_ambig else out
+
+
+def average_distance_loss(pred, target, weight, point, symmetry, margin):
+    pred = _f32(pred); target = _f32(target); weight = _f32(weight); point = _f32(point); symmetry = _f32(symmetry)
+    N = pred.shape[0]
+    C, P = point.shape[0], point.shape[1]
+    loss = ctypes.c_float(0)
+    diff = np.zeros((N, 4 * C), np.float32)
+    near = ctypes.c_int(0)
+    lib().pcnn_oracle_average_distance(_p(pred), _p(target), _p(weight), _p(point), _p(symmetry), N, C, P,
+                                       ctypes.c_float(margin), ctypes.byref(loss), _p(diff), ctypes.byref(near))
+    return np.array([loss.value], np.float32), diff

@@ -1,0 +1,2 @@
+// shim: see oracle/ref_shim/ref_shim.h
+#include "ref_shim.h"

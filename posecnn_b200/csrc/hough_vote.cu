@@ -1,0 +1,964 @@
+// hough_vote.cu — Houghvotinggpu for sm_100a, whole batch per call, no host round trips.
+//
+// Behavioural spec: lib/hough_voting_gpu_layer/hough_voting_gpu_op.cu.cc:253-333 (vote
+// predicate: cosine cone > inlier, clipped to a depth-dependent square), :335-383 (maxima),
+// :386-576 (ROI / pose rows), hough_voting_gpu_op.cc:321-428 (batch loop, MAX_ROI/B cap,
+// dummy row).  See DESIGN.md §3 for the algorithm; in short:
+//
+//   The reference evaluates the predicate for every (cell, sampled pixel) pair — a gather of
+//   count*H*W*(N/skip) cosine tests.  Here each sampled pixel scatters its vote set instead.
+//   On one image row the vote set of a pixel is (cone ∩ row ∩ square) = ONE interval of
+//   cells, so a pixel contributes "+1 at the first cell, -1 after the last cell" to a
+//   per-row difference array, and an inclusive prefix sum along the row yields exactly the
+//   vote counts.  Interval end points are estimated analytically (two boundary rays) and
+//   then snapped with the reference's own fp32 predicate, so the result equals the per-cell
+//   evaluation wherever that predicate is monotone along the row (everywhere outside
+//   rounding distance of the threshold).
+//
+//   k_hist     per-chunk class histogram (+ zero-fill of the output buffers)
+//   k_scan     per-image exclusive scan of chunk histograms, class filter (>label_threshold)
+//   k_emit     deterministic raster-order ranks; every skip-th pixel of a class becomes a
+//              32-byte sample record (direction, depth, window, boundary-ray slopes)
+//   k_worklist (image, class, 32-row band) work items inside each class's vote bounding box
+//   k_vote     persistent CTAs: difference array of a band in shared memory, shared-memory
+//              atomics (2 per sample-row), row prefix scan fused with the arg-max
+//   k_select / k_localmax   maxima (first arg-max per class, or 7x7 local maxima)
+//   k_celldata per selected cell: exact recount, mean depth, box extents (second pass of the
+//              reference kernel, done only for selected cells)
+//   k_finalize ROI cap, row offsets, ROI / pose / target / weight / domain rows
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pcnn {
+namespace hough {
+
+constexpr int kChunk = 2048;      // pixels per CTA in k_hist / k_emit
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCandCapThr = 4096; // candidate capacity per image in threshold mode
+constexpr int kMaxM = 16383;
+
+struct __align__(16) Sample {
+    int xy;       // x | y << 16
+    float u, v;   // predicted direction (vertex channels 3c, 3c+1)
+    float n1;     // |(u,v)| rounded like the reference (angle_distance, .cu.cc:36)
+    float k1, k2; // dx = dy * k for the two boundary rays of the cone
+    int mflags;   // window half-size m (cells with |dx|,|dy| <= m pass `< threshold`) | flags << 16
+    float d;      // exp(vertex channel 3c+2)
+};
+static_assert(sizeof(Sample) == 32, "sample record is two 16-byte vectors");
+
+struct Layout {
+    int nchunks, nbands, R, samp_cap, cand_cap;
+    size_t chunk_hist, cls_size, cls_slot, cls_nsamp, cls_soff, slot_cls, img_count, bbox, samples, band_res, work,
+        work_ctr, cand_key, cand_val, cand_n, cand_data, votes, total;
+};
+
+static int band_rows(int W)
+{
+    // difference array of one band: R rows x (W + 3) ints, kept under ~100 KB so two CTAs fit per SM
+    int R = 32;
+    while (R > 1 && (size_t)R * (W + 3) * 4 > 100 * 1024) R >>= 1;
+    return R;
+}
+
+static Layout make_layout(int B, int H, int W, int C, int skip, bool want_votes, bool threshold_mode)
+{
+    Layout L;
+    size_t HW = (size_t)H * W;
+    L.nchunks = (int)((HW + kChunk - 1) / kChunk);
+    L.R = band_rows(W);
+    L.nbands = (H + L.R - 1) / L.R;
+    L.samp_cap = (int)((HW + skip - 1) / skip) + C;
+    L.cand_cap = threshold_mode ? kCandCapThr : C;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    L.chunk_hist = take(sizeof(int) * (size_t)B * L.nchunks * C);
+    L.cls_size = take(sizeof(int) * (size_t)B * C);
+    L.cls_slot = take(sizeof(int) * (size_t)B * C);
+    L.cls_nsamp = take(sizeof(int) * (size_t)B * C);
+    L.cls_soff = take(sizeof(int) * (size_t)B * C);
+    L.slot_cls = take(sizeof(int) * (size_t)B * C);
+    L.img_count = take(sizeof(int) * (size_t)B);
+    L.bbox = take(sizeof(int) * (size_t)B * C * 4);
+    L.samples = take(sizeof(Sample) * (size_t)B * L.samp_cap);
+    L.band_res = take(sizeof(int2) * (size_t)B * C * L.nbands);
+    L.work = take(sizeof(int) * (size_t)B * C * L.nbands);
+    L.work_ctr = take(sizeof(int) * 4);
+    L.cand_key = take(sizeof(int) * (size_t)B * L.cand_cap);
+    L.cand_val = take(sizeof(int) * (size_t)B * L.cand_cap);
+    L.cand_n = take(sizeof(int) * (size_t)B);
+    L.cand_data = take(sizeof(float4) * (size_t)B * L.cand_cap);
+    L.votes = want_votes ? take(sizeof(float) * (size_t)B * C * HW) : o;
+    L.total = o;
+    return L;
+}
+
+// ----------------------------------------------------------------------------------------
+// geometry shared by the kernels (formulas of .cu.cc:32-42, 73-172 with the rounding that
+// nvcc's default contraction gives the reference: a*b + c*d -> fma(a, b, RN(c*d)))
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float project_box(int cls, const float* __restrict__ extents,
+                                             const float* __restrict__ meta, float distance, float factor)
+{
+    float xHalf = extents[cls * 3 + 0] * 0.5f;
+    float yHalf = extents[cls * 3 + 1] * 0.5f;
+    float zHalf = extents[cls * 3 + 2] * 0.5f;
+    float fx = meta[0], fy = meta[4], px = meta[2], py = meta[5];
+    float minX = 1e8f, maxX = -1e8f, minY = 1e8f, maxY = -1e8f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float X = (i & 1) ? -xHalf : xHalf;
+        float Y = (i & 2) ? -yHalf : yHalf;
+        float Z = __fadd_rn((i & 4) ? -zHalf : zHalf, distance);
+        float x = __fmaf_rn(fx, __fdiv_rn(X, Z), px);
+        float y = __fmaf_rn(fy, __fdiv_rn(Y, Z), py);
+        minX = fminf(minX, x); minY = fminf(minY, y);
+        maxX = fmaxf(maxX, x); maxY = fmaxf(maxY, y);
+    }
+    float width = __fadd_rn(__fsub_rn(maxX, minX), 1.f);
+    float height = __fadd_rn(__fsub_rn(maxY, minY), 1.f);
+    return __fmul_rn(fmaxf(width, height), factor);
+}
+
+// the reference predicate, bit for bit: dot / (n1 * n2) > inlier  (angle_distance, .cu.cc:32-42)
+__device__ __forceinline__ bool pred_exact(float u, float v, float n1, float dx, float dy, float inlier)
+{
+    float n2 = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    float dot = __fmaf_rn(u, dx, __fmul_rn(v, dy));
+    float c = __fdiv_rn(dot, __fmul_rn(n1, n2));
+    return c > inlier;
+}
+
+// same decision, cheap: sign of dot - inlier*n1*|d| when it is far (4e-6 relative) from zero,
+// otherwise the exact evaluation.  vdy = RN(v*dy), dy2 = dy*dy, tn1 = inlier*n1.
+__device__ __forceinline__ bool pred_fast(float u, float v, float n1, float tn1, float dx, float dy, float vdy,
+                                          float dy2, float inlier)
+{
+    float s2 = __fmaf_rn(dx, dx, dy2);
+    float dot = __fmaf_rn(u, dx, vdy);
+    float rhs = tn1 * (s2 * rsqrtf(s2));
+    float g = dot - rhs;
+    if (fabsf(g) > 4e-6f * rhs) return g > 0.f;
+    return pred_exact(u, v, n1, dx, dy, inlier);
+}
+
+// ----------------------------------------------------------------------------------------
+// k_hist: per-chunk class histogram; also zero-fills the five output buffers + counters
+// ----------------------------------------------------------------------------------------
+struct ZeroList {
+    float* p[5];
+    unsigned n[5];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restrict__ chunk_hist, ZeroList z)
+{
+    extern __shared__ int sh[];
+    const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x, lane = t & 31;
+    // zero-fill outputs (reset_outputs, .cu.cc:579-588), spread over the whole grid
+    {
+        unsigned gid = (blockIdx.y * gridDim.x + blockIdx.x) * kThreads + t;
+        unsigned gsz = gridDim.x * gridDim.y * kThreads;
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            for (unsigned i = gid; i < z.n[k]; i += gsz) z.p[k][i] = 0.f;
+    }
+    for (int c = t; c < C; c += kThreads) sh[c] = 0;
+    __syncthreads();
+    const int* lab = label + (size_t)b * HW;
+#pragma unroll
+    for (int j = 0; j < kChunk / kThreads; j++) {
+        int p = chunk * kChunk + j * kThreads + t;
+        int cls = p < HW ? lab[p] : -1;
+        bool valid = cls > 0 && cls < C;
+        unsigned peers = __match_any_sync(0xffffffffu, valid ? cls : -1);
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh[cls], __popc(peers));
+    }
+    __syncthreads();
+    int* out = chunk_hist + ((size_t)b * nchunks + chunk) * C;
+    for (int c = t; c < C; c += kThreads) out[c] = sh[c];
+}
+
+// ----------------------------------------------------------------------------------------
+// k_scan: exclusive scan over chunks per (image, class); class filter and sample offsets
+// (class_indexes of .cu.cc:650-663, built on the device)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_scan(int C, int nchunks, int skip, int label_thr, int* __restrict__ chunk_hist, int* __restrict__ cls_size,
+       int* __restrict__ cls_slot, int* __restrict__ cls_nsamp, int* __restrict__ cls_soff,
+       int* __restrict__ slot_cls, int* __restrict__ img_count, int* __restrict__ bbox, int* __restrict__ cand_n,
+       int* __restrict__ work_ctr)
+{
+    const int b = blockIdx.x, t = threadIdx.x;
+    for (int c = t; c < C; c += kThreads) {
+        int* h = chunk_hist + (size_t)b * nchunks * C + c;
+        int run = 0;
+        for (int k = 0; k < nchunks; k++) {
+            int v = h[(size_t)k * C];
+            h[(size_t)k * C] = run;
+            run += v;
+        }
+        cls_size[b * C + c] = run;
+    }
+    __syncthreads();
+    if (t == 0) {
+        int slot = 0, soff = 0;
+        for (int c = 0; c < C; c++) {
+            int sz = cls_size[b * C + c];
+            if (c > 0 && sz > label_thr) {
+                int ns = (sz + skip - 1) / skip;
+                cls_slot[b * C + c] = slot;
+                slot_cls[b * C + slot] = c;
+                cls_nsamp[b * C + c] = ns;
+                cls_soff[b * C + c] = soff;
+                soff += ns;
+                slot++;
+            } else {
+                cls_slot[b * C + c] = -1;
+                cls_nsamp[b * C + c] = 0;
+                cls_soff[b * C + c] = 0;
+            }
+            int* bb = bbox + ((size_t)b * C + c) * 4;
+            bb[0] = 0x7fffffff; bb[1] = -1; bb[2] = 0x7fffffff; bb[3] = -1;
+        }
+        img_count[b] = slot;
+        cand_n[b] = 0;
+        if (b == 0) { work_ctr[0] = 0; work_ctr[1] = 0; }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_emit: canonical (ascending pixel index) rank of every foreground pixel within its class;
+// pixels with rank % skip == 0 become samples (the sub-sampling of .cu.cc:269 applied to the
+// canonical list order of SURVEY.md §8(c))
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const float* __restrict__ extents,
+       const float* __restrict__ meta_all, int H, int W, int C, int num_meta, int nchunks, int skip, float inlier,
+       const int* __restrict__ chunk_prefix, const int* __restrict__ cls_slot, const int* __restrict__ cls_soff,
+       Sample* __restrict__ samples, int samp_cap, int* __restrict__ bbox)
+{
+    extern __shared__ int wh[];  // [kWarps][C]
+    const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int HW = H * W;
+    const int* lab = label + (size_t)b * HW;
+    const int base = chunk * kChunk + w * (kChunk / kWarps);
+    int labs[kChunk / kThreads];
+#pragma unroll
+    for (int s = 0; s < kChunk / kThreads; s++) {
+        int p = base + s * 32 + lane;
+        int cls = p < HW ? lab[p] : -1;
+        if (!(cls > 0 && cls < C) || cls_slot[b * C + cls] < 0) cls = -1;
+        labs[s] = cls;
+    }
+    for (int i = t; i < kWarps * C; i += kThreads) wh[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < kChunk / kThreads; s++) {
+        int cls = labs[s];
+        unsigned peers = __match_any_sync(0xffffffffu, cls);
+        if (cls >= 0 && lane == __ffs(peers) - 1) wh[w * C + cls] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += kThreads) {
+        int run = chunk_prefix[((size_t)b * nchunks + chunk) * C + c];
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ww++) {
+            int tmp = wh[ww * C + c];
+            wh[ww * C + c] = run;
+            run += tmp;
+        }
+    }
+    __syncthreads();
+    const float* meta = meta_all + (size_t)b * num_meta;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int s = 0; s < kChunk / kThreads; s++) {
+        int cls = labs[s];
+        unsigned peers = __match_any_sync(0xffffffffu, cls);
+        int rank = 0;
+        if (cls >= 0) rank = wh[w * C + cls] + __popc(peers & lt);
+        __syncwarp();
+        if (cls >= 0 && lane == __ffs(peers) - 1) wh[w * C + cls] += __popc(peers);
+        __syncwarp();
+        if (cls >= 0 && rank % skip == 0) {
+            int p = base + s * 32 + lane;
+            int x = p % W, y = p / W;
+            size_t off = (size_t)3 * cls + (size_t)3 * C * ((size_t)b * HW + p);
+            float u = vertex[off], v = vertex[off + 1], z = vertex[off + 2];
+            float d = expf(z);
+            float n1 = __fsqrt_rn(__fmaf_rn(u, u, __fmul_rn(v, v)));
+            float thr = project_box(cls, extents, meta, d, 0.6f);
+            int m = -1;
+            if (thr == thr && n1 > 0.f && n1 < INFINITY) {
+                float mf = fminf(fmaxf(ceilf(thr) - 1.f, -1.f), (float)kMaxM);
+                m = (int)mf;
+            }
+            // boundary rays of the cone: axis rotated by +-acos(inlier)
+            float inv = 1.f / n1, uh = u * inv, vh = v * inv;
+            float ca = inlier, sa = sqrtf(fmaxf(1.f - ca * ca, 0.f));
+            float r1x = ca * uh - sa * vh, r1y = ca * vh + sa * uh;
+            float r2x = ca * uh + sa * vh, r2y = ca * vh - sa * uh;
+            float k1 = r1x / r1y, k2 = r2x / r2y;
+            int flags = (r1y > 0.f ? 1 : 0) | (r1y < 0.f ? 2 : 0) | (r2y > 0.f ? 4 : 0) | (r2y < 0.f ? 8 : 0) |
+                        ((r2x - r2y * k1) > 0.f ? 16 : 0) | ((r1x - r1y * k2) > 0.f ? 32 : 0);
+            Sample rec;
+            rec.xy = x | (y << 16);
+            rec.u = u; rec.v = v; rec.n1 = n1; rec.k1 = k1; rec.k2 = k2;
+            rec.mflags = (m & 0xffff) | (flags << 16);
+            rec.d = d;
+            Sample* dst = samples + (size_t)b * samp_cap + cls_soff[b * C + cls] + rank / skip;
+            reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(&rec)[0];
+            reinterpret_cast<float4*>(dst)[1] = reinterpret_cast<const float4*>(&rec)[1];
+            if (m >= 0) {
+                int* bb = bbox + ((size_t)b * C + cls) * 4;
+                atomicMin(&bb[0], max(y - m, 0));
+                atomicMax(&bb[1], min(y + m, H - 1));
+                atomicMin(&bb[2], max(x - m, 0));
+                atomicMax(&bb[3], min(x + m, W - 1));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_worklist: (image, slot, band) items for every band that intersects a class's vote box
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_worklist(int B, int C, int R, int nbands, const int* __restrict__ img_count, const int* __restrict__ slot_cls,
+           const int* __restrict__ bbox, int* __restrict__ work, int* __restrict__ work_ctr)
+{
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * C; i += kThreads) {
+        int b = i / C, slot = i % C;
+        if (slot >= img_count[b]) continue;
+        int c = slot_cls[b * C + slot];
+        const int* bb = bbox + ((size_t)b * C + c) * 4;
+        if (bb[1] < bb[0]) continue;
+        int lo = bb[0] / R, hi = bb[1] / R;
+        int pos = atomicAdd(&s_n, hi - lo + 1);
+        for (int k = lo; k <= hi; k++) work[pos++] = (b * C + slot) * nbands + k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { work_ctr[0] = 0; work_ctr[1] = s_n; }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_vote: persistent CTAs; one (image, class, band) difference array in shared memory
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restrict__ slot_cls,
+       const int* __restrict__ cls_nsamp, const int* __restrict__ cls_soff, const int* __restrict__ bbox,
+       const Sample* __restrict__ samples, int samp_cap, const int* __restrict__ work, int* __restrict__ work_ctr,
+       int2* __restrict__ band_res, float* __restrict__ votes_out)
+{
+    extern __shared__ int D[];
+    __shared__ int s_item;
+    __shared__ int s_red_val[kWarps];
+    __shared__ int s_red_idx[kWarps];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int total = work_ctr[1];
+    while (true) {
+        __syncthreads();
+        if (t == 0) s_item = atomicAdd(&work_ctr[0], 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total) break;
+        const int key = work[item];
+        const int band = key % nbands, bs = key / nbands, slot = bs % C, b = bs / C;
+        const int c = slot_cls[b * C + slot];
+        const int* bb = bbox + ((size_t)b * C + c) * 4;
+        const int xlo = bb[2], xhi = bb[3];
+        const int Wd = xhi - xlo + 1;
+        const int stride = (Wd + 1) | 1;
+        const int r0 = band * R;
+        const int nrows = min(R, H - r0);
+        for (int i = t; i < R * stride; i += kThreads) D[i] = 0;
+        __syncthreads();
+
+        const int ns = cls_nsamp[b * C + c];
+        const Sample* S = samples + (size_t)b * samp_cap + cls_soff[b * C + c];
+        const int cy = r0 + lane;
+        int* Drow = D + lane * stride - xlo;
+        for (int s = w; s < ns; s += kWarps) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(S + s));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(S + s) + 1);
+            const int xy = __float_as_int(q0.x);
+            const int x = xy & 0xffff, y = xy >> 16;
+            const int mflags = __float_as_int(q1.z);
+            const int m = (int)(short)(mflags & 0xffff);
+            const int idy = cy - y;
+            if (lane >= nrows || m < 0 || abs(idy) > m) continue;
+            const float u = q0.y, v = q0.z, n1 = q0.w;
+            const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
+            const float tn1 = inlier * n1;
+            const float dy = (float)idy;
+            int a, e;  // candidate interval [a, e]
+            if (idy == 0) {
+                // on the pixel's own row cos = sign(dx) * u / n1 (the pixel itself gives 0/0 = NaN: no vote)
+                if (pred_exact(u, v, n1, 1.f, 0.f, inlier)) { a = x + 1; e = wmax; }
+                else if (pred_exact(u, v, n1, -1.f, 0.f, inlier)) { a = wmin; e = x - 1; }
+                else continue;
+                if (a > e) continue;
+            } else {
+                const int fl = mflags >> 16;
+                const bool v1 = idy > 0 ? (fl & 1) : (fl & 2);
+                const bool v2 = idy > 0 ? (fl & 4) : (fl & 8);
+                if (!v1 && !v2) continue;
+                const float h1 = dy * q1.x, h2 = dy * q1.y;
+                float lo, hi;
+                if (v1 && v2) { lo = fminf(h1, h2); hi = fmaxf(h1, h2); }
+                else if (v1) { if (fl & 16) { lo = h1; hi = 1e9f; } else { lo = -1e9f; hi = h1; } }
+                else { if (fl & 32) { lo = h2; hi = 1e9f; } else { lo = -1e9f; hi = h2; } }
+                lo = fminf(fmaxf(lo, -40000.f), 40000.f);
+                hi = fminf(fmaxf(hi, -40000.f), 40000.f);
+                a = max(wmin, x + (int)ceilf(lo));
+                e = min(wmax, x + (int)floorf(hi));
+                // snap both ends with the reference predicate
+                const float vdy = __fmul_rn(v, dy), dy2 = dy * dy;
+                auto P = [&](int cx) { return pred_fast(u, v, n1, tn1, (float)(cx - x), dy, vdy, dy2, inlier); };
+                if (a > e) {
+                    // estimated empty: the only cells that can still pass sit at the estimate itself
+                    int c0 = min(max(a, wmin), wmax);
+                    if (P(c0)) { a = e = c0; }
+                    else {
+                        int c1 = min(max(e, wmin), wmax);
+                        if (c1 != c0 && P(c1)) { a = e = c1; } else continue;
+                    }
+                }
+                while (a > wmin && P(a - 1)) a--;
+                while (a <= e && !P(a)) a++;
+                if (a > e) continue;
+                while (e < wmax && P(e + 1)) e++;
+                while (e > a && !P(e)) e--;
+            }
+            atomicAdd(&Drow[a], 1);
+            atomicAdd(&Drow[e + 1], -1);
+        }
+        __syncthreads();
+
+        // row prefix sums fused with the arg-max (first maximum in flat index order)
+        int best_val = -1, best_idx = 0x7fffffff;
+        for (int row = w; row < nrows; row += kWarps) {
+            int carry = 0;
+            int* Dr = D + row * stride;
+            for (int x0 = 0; x0 < Wd; x0 += 32) {
+                int xi = x0 + lane;
+                int val = xi < Wd ? Dr[xi] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int nb = __shfl_up_sync(0xffffffffu, val, o);
+                    if (lane >= o) val += nb;
+                }
+                val += carry;
+                carry = __shfl_sync(0xffffffffu, val, 31);
+                if (xi < Wd) {
+                    if (votes_out) Dr[xi] = val;
+                    int idx = (r0 + row) * W + xlo + xi;
+                    if (val > best_val) { best_val = val; best_idx = idx; }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int ov = __shfl_xor_sync(0xffffffffu, best_val, o);
+            int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            if (ov > best_val || (ov == best_val && oi < best_idx)) { best_val = ov; best_idx = oi; }
+        }
+        if (lane == 0) { s_red_val[w] = best_val; s_red_idx[w] = best_idx; }
+        __syncthreads();
+        if (t == 0) {
+            int bv = s_red_val[0], bi = s_red_idx[0];
+            for (int k = 1; k < kWarps; k++)
+                if (s_red_val[k] > bv || (s_red_val[k] == bv && s_red_idx[k] < bi)) { bv = s_red_val[k]; bi = s_red_idx[k]; }
+            band_res[(size_t)(b * C + slot) * nbands + band] = make_int2(bv, bi);
+        }
+        if (votes_out) {
+            float* plane = votes_out + ((size_t)b * C + c) * H * W;
+            for (int i = t; i < nrows * W; i += kThreads) {
+                int row = i / W, x = i % W;
+                float val = (x >= xlo && x <= xhi) ? (float)D[row * stride + x - xlo] : 0.f;
+                plane[(size_t)(r0 + row) * W + x] = val;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_select: default mode — first arg-max of each present class (thrust::max_element,
+// .cu.cc:752-762), first `cap` classes (.cu.cc:773-774)
+// ----------------------------------------------------------------------------------------
+__global__ void k_select(int C, int HW, int R, int nbands, int cap, int cand_cap, const int* __restrict__ img_count,
+                         const int* __restrict__ slot_cls, const int* __restrict__ bbox,
+                         const int2* __restrict__ band_res, int* __restrict__ cand_key, int* __restrict__ cand_val,
+                         int* __restrict__ cand_n)
+{
+    const int b = blockIdx.x;
+    const int count = img_count[b];
+    const int n = min(min(count, cap), cand_cap);
+    for (int slot = threadIdx.x; slot < n; slot += blockDim.x) {
+        int c = slot_cls[b * C + slot];
+        const int* bb = bbox + ((size_t)b * C + c) * 4;
+        int bv = 0, bi = 0;
+        if (bb[1] >= bb[0]) {
+            int lo = bb[0] / R, hi = bb[1] / R;
+            bv = -1; bi = 0x7fffffff;
+            for (int k = lo; k <= hi; k++) {
+                int2 r = band_res[(size_t)(b * C + slot) * nbands + k];
+                if (r.x > bv || (r.x == bv && r.y < bi)) { bv = r.x; bi = r.y; }
+            }
+            if (bv <= 0) { bv = 0; bi = 0; }  // empty plane: max_element returns the first element
+        }
+        cand_key[(size_t)b * cand_cap + slot] = slot * HW + bi;
+        cand_val[(size_t)b * cand_cap + slot] = bv;
+    }
+    if (threadIdx.x == 0) cand_n[b] = n;
+}
+
+// ----------------------------------------------------------------------------------------
+// k_localmax: threshold mode — vote > threshold and no strictly greater vote in the clipped
+// 7x7 window (.cu.cc:351-367); the box / density tests need hough_data and run in k_finalize
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_localmax(int H, int W, int C, int R, float vote_thr, int cand_cap, const int* __restrict__ img_count,
+           const int* __restrict__ slot_cls, const int* __restrict__ bbox, const float* __restrict__ votes,
+           int* __restrict__ cand_key, int* __restrict__ cand_val, int* __restrict__ cand_n, int* __restrict__ status)
+{
+    const int b = blockIdx.z, slot = blockIdx.y;
+    if (slot >= img_count[b]) return;
+    const int c = slot_cls[b * C + slot];
+    const int* bb = bbox + ((size_t)b * C + c) * 4;
+    if (bb[1] < bb[0]) return;
+    const int ylo = (bb[0] / R) * R, yhi = min(H - 1, (bb[1] / R) * R + R - 1);  // rows written by k_vote
+    const int p = blockIdx.x * kThreads + threadIdx.x;
+    if (p >= H * W) return;
+    const int cx = p % W, cy = p / W;
+    if (cy < ylo || cy > yhi) return;
+    const float* plane = votes + ((size_t)b * C + c) * H * W;
+    const float val = plane[p];
+    if (!(val > vote_thr)) return;
+    for (int x = cx - 3; x <= cx + 3; x++)
+        for (int y = cy - 3; y <= cy + 3; y++)
+            if (x >= 0 && x < W && y >= ylo && y <= yhi && plane[y * W + x] > val) return;
+    int pos = atomicAdd(&cand_n[b], 1);
+    if (pos < cand_cap) {
+        cand_key[(size_t)b * cand_cap + pos] = slot * (H * W) + p;
+        cand_val[(size_t)b * cand_cap + pos] = (int)val;
+    } else if (status) {
+        atomicOr(&status[0], 1);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_celldata: per candidate cell, the reference's per-cell loops (.cu.cc:266-331): exact
+// recount, mean depth, second pass for the box extents
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_celldata(int B, int H, int W, int C, int num_meta, float inlier, int cand_cap, const float* __restrict__ extents,
+           const float* __restrict__ meta_all, const int* __restrict__ slot_cls, const int* __restrict__ cls_nsamp,
+           const int* __restrict__ cls_soff, const Sample* __restrict__ samples, int samp_cap,
+           const int* __restrict__ cand_key, const int* __restrict__ cand_n, float4* __restrict__ cand_data)
+{
+    __shared__ float s_sum[kThreads];
+    __shared__ int s_cnt[kThreads];
+    __shared__ float s_thr2;
+    const int t = threadIdx.x;
+    const int HW = H * W;
+    for (int b = 0; b < B; b++) {
+        const int n = min(cand_n[b], cand_cap);
+        for (int i = blockIdx.x; i < n; i += gridDim.x) {
+            const int key = cand_key[(size_t)b * cand_cap + i];
+            const int slot = key / HW, p = key % HW;
+            const int c = slot_cls[b * C + slot];
+            const int cx = p % W, cy = p / W;
+            const int ns = cls_nsamp[b * C + c];
+            const Sample* S = samples + (size_t)b * samp_cap + cls_soff[b * C + c];
+            float sum = 0.f;
+            int cnt = 0;
+            for (int s = t; s < ns; s += kThreads) {
+                const Sample q = S[s];
+                const int x = q.xy & 0xffff, y = q.xy >> 16;
+                const int m = (int)(short)(q.mflags & 0xffff);
+                if (m < 0 || abs(x - cx) > m || abs(y - cy) > m) continue;
+                if (pred_exact(q.u, q.v, q.n1, (float)(cx - x), (float)(cy - y), inlier)) { cnt++; sum += q.d; }
+            }
+            s_sum[t] = sum; s_cnt[t] = cnt;
+            __syncthreads();
+            for (int o = kThreads / 2; o > 0; o >>= 1) {
+                if (t < o) { s_sum[t] += s_sum[t + o]; s_cnt[t] += s_cnt[t + o]; }
+                __syncthreads();
+            }
+            const int votes = s_cnt[0];
+            float dist = 0.f;
+            if (votes > 0) dist = __fdiv_rn(s_sum[0], (float)votes);
+            if (t == 0) s_thr2 = votes > 0 ? project_box(c, extents, meta_all + (size_t)b * num_meta, dist, 0.6f) : 0.f;
+            __syncthreads();
+            const float thr2 = s_thr2;
+            float bbw = -1.f, bbh = -1.f;
+            if (votes > 0) {
+                for (int s = t; s < ns; s += kThreads) {
+                    const Sample q = S[s];
+                    const int x = q.xy & 0xffff, y = q.xy >> 16;
+                    const float dx = fabsf((float)(x - cx)), dy = fabsf((float)(y - cy));
+                    if (!(dx < thr2 && dy < thr2)) continue;
+                    if (q.n1 > 0.f && pred_exact(q.u, q.v, q.n1, (float)(cx - x), (float)(cy - y), inlier)) {
+                        bbw = fmaxf(bbw, dx);
+                        bbh = fmaxf(bbh, dy);
+                    }
+                }
+            }
+            __syncthreads();
+            s_sum[t] = bbw;
+            reinterpret_cast<float*>(s_cnt)[t] = bbh;
+            __syncthreads();
+            for (int o = kThreads / 2; o > 0; o >>= 1) {
+                if (t < o) {
+                    s_sum[t] = fmaxf(s_sum[t], s_sum[t + o]);
+                    reinterpret_cast<float*>(s_cnt)[t] =
+                        fmaxf(reinterpret_cast<float*>(s_cnt)[t], reinterpret_cast<float*>(s_cnt)[t + o]);
+                }
+                __syncthreads();
+            }
+            if (t == 0) {
+                float4 r;
+                if (votes > 0) {
+                    r.x = dist;
+                    r.y = 2.f * reinterpret_cast<float*>(s_cnt)[0];
+                    r.z = 2.f * s_sum[0];
+                } else {
+                    r.x = 0.f; r.y = 0.f; r.z = 0.f;  // hough_data stays zero (.cu.cc:296)
+                }
+                r.w = (float)votes;
+                cand_data[(size_t)b * cand_cap + i] = r;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_finalize: ROI cap, row offsets, rows (compute_rois_kernel, .cu.cc:386-576)
+// ----------------------------------------------------------------------------------------
+__device__ float box_overlap(int cls, const float* __restrict__ extents, const float* __restrict__ meta,
+                             const float* __restrict__ pose, const float* box)
+{
+    // compute_box_overlap, .cu.cc:123-172: rotate the 8 extent corners by the gt quaternion
+    // (unit-quaternion rotation matrix), translate, project, IoU with the predicted box
+    float xHalf = extents[cls * 3 + 0] * 0.5f, yHalf = extents[cls * 3 + 1] * 0.5f, zHalf = extents[cls * 3 + 2] * 0.5f;
+    float w = pose[6], x = pose[7], y = pose[8], z = pose[9];
+    float tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y,
+          tzz = tz * z;
+    float R0 = 1 - (tyy + tzz), R1 = txy - twz, R2 = txz + twy, R3 = txy + twz, R4 = 1 - (txx + tzz), R5 = tyz - twx,
+          R6 = txz - twy, R7 = tyz + twx, R8 = 1 - (txx + tyy);
+    float fx = meta[0], fy = meta[4], px = meta[2], py = meta[5];
+    float x1 = 1e8f, x2 = -1e8f, y1 = 1e8f, y2 = -1e8f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float bx = (i & 1) ? -xHalf : xHalf, by = (i & 2) ? -yHalf : yHalf, bz = (i & 4) ? -zHalf : zHalf;
+        float X = __fmaf_rn(R2, bz, __fmaf_rn(R1, by, R0 * bx)) + pose[10];
+        float Y = __fmaf_rn(R5, bz, __fmaf_rn(R4, by, R3 * bx)) + pose[11];
+        float Z = __fmaf_rn(R8, bz, __fmaf_rn(R7, by, R6 * bx)) + pose[12];
+        float xx = __fmaf_rn(fx, __fdiv_rn(X, Z), px), yy = __fmaf_rn(fy, __fdiv_rn(Y, Z), py);
+        x1 = fminf(x1, xx); y1 = fminf(y1, yy); x2 = fmaxf(x2, xx); y2 = fmaxf(y2, yy);
+    }
+    float left = fmaxf(box[0], x1), right = fminf(box[2], x2), top = fmaxf(box[1], y1), bottom = fminf(box[3], y2);
+    float iw = fmaxf(right - left + 1, 0.f), ih = fmaxf(bottom - top + 1, 0.f);
+    float inter = iw * ih;
+    float Sa = (box[2] - box[0] + 1) * (box[3] - box[1] + 1), Sb = (x2 - x1 + 1) * (y2 - y1 + 1);
+    return inter / (Sa + Sb - inter);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_finalize(int B, int H, int W, int C, int num_meta, int num_gt, int is_train, int cap, int cand_cap, int threshold_mode,
+           float per_thr, const float* __restrict__ extents, const float* __restrict__ meta_all,
+           const float* __restrict__ gt, const int* __restrict__ slot_cls, const int* __restrict__ cand_key,
+           const int* __restrict__ cand_val, const int* __restrict__ cand_n, const float4* __restrict__ cand_data,
+           int* __restrict__ sel /* [B][PCNN_MAX_ROI] candidate index of each kept maximum */,
+           int* __restrict__ sel_n /* [B+1] counts then row offsets */, float* __restrict__ top_box,
+           float* __restrict__ top_pose, float* __restrict__ top_target, float* __restrict__ top_weight,
+           int* __restrict__ top_domain, int* __restrict__ num_rois, int* __restrict__ status)
+{
+    __shared__ int s_off[PCNN_MAX_ROI + 2];
+    __shared__ int s_pass;
+    const int t = threadIdx.x;
+    const int HW = H * W;
+    // 1. kept maxima per image, canonical order
+    for (int b = 0; b < B; b++) {
+        const int n = min(cand_n[b], cand_cap);
+        if (!threshold_mode) {
+            for (int i = t; i < n; i += kThreads) sel[b * PCNN_MAX_ROI + i] = i;
+            if (t == 0) sel_n[b] = n;
+        } else {
+            if (t == 0) s_pass = 0;
+            __syncthreads();
+            for (int i = t; i < n; i += kThreads) {
+                const float4 d = cand_data[(size_t)b * cand_cap + i];
+                // .cu.cc:351 (box > 0) and :370 (votes / (h*w) < perThreshold rejects)
+                bool pass = d.y > 0.f && d.z > 0.f && !(__fdiv_rn(d.w, d.y * d.z) < per_thr);
+                if (!pass) continue;
+                const int key = cand_key[(size_t)b * cand_cap + i];
+                int rank = 0;
+                for (int j = 0; j < n; j++) {
+                    const float4 e = cand_data[(size_t)b * cand_cap + j];
+                    bool pj = e.y > 0.f && e.z > 0.f && !(__fdiv_rn(e.w, e.y * e.z) < per_thr);
+                    if (pj && cand_key[(size_t)b * cand_cap + j] < key) rank++;
+                }
+                atomicAdd(&s_pass, 1);
+                if (rank < cap) sel[b * PCNN_MAX_ROI + rank] = i;
+            }
+            __syncthreads();
+            if (t == 0) sel_n[b] = min(s_pass, cap);
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // 2. row offsets (images in order: the reference loops the batch serially, .cc:369-377)
+    if (t == 0) {
+        int run = 0;
+        for (int b = 0; b < B; b++) { s_off[b] = run; run += sel_n[b]; }
+        s_off[B] = run;
+        *num_rois = run * (is_train ? 9 : 1);
+    }
+    __syncthreads();
+    const int total = s_off[B];
+    // 3. rows
+    for (int r = t; r < total; r += kThreads) {
+        int b = 0;
+        while (s_off[b + 1] <= r) b++;
+        const int i = sel[b * PCNN_MAX_ROI + (r - s_off[b])];
+        const int key = cand_key[(size_t)b * cand_cap + i];
+        const int slot = key / HW, p = key % HW;
+        const int cls = slot_cls[b * C + slot];
+        const int x = p % W, y = p / W;
+        const float4 d = cand_data[(size_t)b * cand_cap + i];
+        const float bb_distance = d.x, bb_height = d.y, bb_width = d.z, votes = d.w;
+        if (status && (int)votes != cand_val[(size_t)b * cand_cap + i]) atomicAdd(&status[1], 1);
+        const float* meta = meta_all + (size_t)b * num_meta;
+        const float fx = meta[0], fy = meta[4], px = meta[2], py = meta[5];
+        const float rx = __fdiv_rn((float)x - px, fx), ry = __fdiv_rn((float)y - py, fy);
+        const float scale = 0.05f;
+        const int nrow = is_train ? 9 : 1;
+        const int roi = r * nrow;
+        float* b0 = top_box + (size_t)roi * 7;
+        // `x - bb_width * (0.5 + scale)` is double arithmetic in the reference (.cu.cc:417-420)
+        const double f = 0.5 + (double)scale;
+        b0[0] = (float)b;
+        b0[1] = (float)cls;
+        b0[2] = (float)((double)x - (double)bb_width * f);
+        b0[3] = (float)((double)y - (double)bb_height * f);
+        b0[4] = (float)((double)x + (double)bb_width * f);
+        b0[5] = (float)((double)y + (double)bb_height * f);
+        b0[6] = votes;
+        for (int k = 0; k < nrow; k++) {
+            float* q = top_pose + (size_t)(roi + k) * 7;
+            q[0] = 1.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f;
+            q[4] = __fmul_rn(rx, bb_distance); q[5] = __fmul_rn(ry, bb_distance); q[6] = bb_distance;
+            if (is_train) top_domain[roi + k] = num_gt == 0 ? 1 : 0;
+        }
+        if (!is_train) continue;
+        for (int g = 0; g < num_gt; g++) {
+            const float* gp = gt + (size_t)g * 13;
+            if (cls == (int)gp[1] && b == (int)gp[0]) {
+                if (box_overlap(cls, extents, meta, gp, b0 + 2) > 0.2f) {
+                    for (int j = 0; j < 9; j++)
+                        for (int k = 0; k < 4; k++) {
+                            top_target[(size_t)(roi + j) * 4 * C + 4 * cls + k] = gp[6 + k];
+                            top_weight[(size_t)(roi + j) * 4 * C + 4 * cls + k] = 1.f;
+                        }
+                    break;
+                }
+            }
+        }
+        const float x1 = b0[2], y1 = b0[3], x2 = b0[4], y2 = b0[5];
+        const float ww = x2 - x1, hh = y2 - y1;
+        // jitter order of .cu.cc:476-554; `x1 - 0.05 * ww` is double arithmetic
+        const int jx[8] = {-1, 1, -1, 1, 0, -1, 0, 1};
+        const int jy[8] = {-1, -1, 1, 1, -1, 0, 1, 0};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float* q = top_box + (size_t)(roi + 1 + j) * 7;
+            q[0] = (float)b;
+            q[1] = (float)cls;
+            q[2] = jx[j] == 0 ? x1 : (float)((double)x1 + jx[j] * (0.05 * (double)ww));
+            q[3] = jy[j] == 0 ? y1 : (float)((double)y1 + jy[j] * (0.05 * (double)hh));
+            q[4] = q[2] + ww;
+            q[5] = q[3] + hh;
+            q[6] = votes;
+        }
+    }
+}
+
+__global__ void k_zero2(float* a, size_t na, float* b, size_t nb)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, g = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = i; k < na / 4; k += g) reinterpret_cast<float4*>(a)[k] = make_float4(0, 0, 0, 0);
+    for (size_t k = na / 4 * 4 + i; k < na; k += g) a[k] = 0.f;
+    for (size_t k = i; k < nb / 4; k += g) reinterpret_cast<float4*>(b)[k] = make_float4(0, 0, 0, 0);
+    for (size_t k = nb / 4 * 4 + i; k < nb; k += g) b[k] = 0.f;
+}
+
+// host side --------------------------------------------------------------------------------
+static int run_front(const Layout& L, char* ws, const int32_t* label, const float* vertex, const float* extents,
+                     const float* meta, int B, int H, int W, int C, int num_meta, float inlier, int label_thr, int skip,
+                     ZeroList z, float* votes_out, cudaStream_t st)
+{
+    int* chunk_hist = (int*)(ws + L.chunk_hist);
+    int* cls_size = (int*)(ws + L.cls_size);
+    int* cls_slot = (int*)(ws + L.cls_slot);
+    int* cls_nsamp = (int*)(ws + L.cls_nsamp);
+    int* cls_soff = (int*)(ws + L.cls_soff);
+    int* slot_cls = (int*)(ws + L.slot_cls);
+    int* img_count = (int*)(ws + L.img_count);
+    int* bbox = (int*)(ws + L.bbox);
+    Sample* samples = (Sample*)(ws + L.samples);
+    int2* band_res = (int2*)(ws + L.band_res);
+    int* work = (int*)(ws + L.work);
+    int* work_ctr = (int*)(ws + L.work_ctr);
+    int* cand_n = (int*)(ws + L.cand_n);
+    const int HW = H * W;
+    dim3 grid(L.nchunks, B);
+    k_hist<<<grid, kThreads, sizeof(int) * C, st>>>(label, HW, C, L.nchunks, chunk_hist, z);
+    k_scan<<<B, kThreads, 0, st>>>(C, L.nchunks, skip, label_thr, chunk_hist, cls_size, cls_slot, cls_nsamp, cls_soff,
+                                   slot_cls, img_count, bbox, cand_n, work_ctr);
+    k_emit<<<grid, kThreads, sizeof(int) * kWarps * C, st>>>(label, vertex, extents, meta, H, W, C, num_meta, L.nchunks,
+                                                             skip, inlier, chunk_hist, cls_slot, cls_soff, samples,
+                                                             L.samp_cap, bbox);
+    k_worklist<<<1, kThreads, 0, st>>>(B, C, L.R, L.nbands, img_count, slot_cls, bbox, work, work_ctr);
+    size_t smem = sizeof(int) * (size_t)L.R * (W + 3);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_set = true;
+    }
+    k_vote<<<2 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, slot_cls, cls_nsamp, cls_soff, bbox,
+                                                samples, L.samp_cap, work, work_ctr, band_res, votes_out);
+    return check_launch("hough front kernels");
+}
+
+static int validate(int B, int H, int W, int C, int skip)
+{
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 2, "hough: need B,H,W >= 1 and C >= 2 (got %d,%d,%d,%d)", B, H, W, C);
+    PCNN_REQUIRE(H <= 16383 && W <= 16383, "hough: image larger than 16383 x 16383 unsupported (got %d x %d)", W, H);
+    PCNN_REQUIRE((long long)C * H * W < 0x7fffffffLL, "hough: C*H*W must fit int32 (reference flat index, .cu.cc:260)");
+    PCNN_REQUIRE(skip >= 1, "hough: skip_pixels must be >= 1 (got %d)", skip);
+    PCNN_REQUIRE(C <= 1024, "hough: at most 1024 classes supported (got %d)", C);
+    return PCNN_OK;
+}
+
+}  // namespace hough
+}  // namespace pcnn
+
+using namespace pcnn;
+using namespace pcnn::hough;
+
+extern "C" int pcnn_hough_vote_workspace_bytes(int B, int H, int W, int C, int skip_pixels, float threshold_vote,
+                                               size_t* bytes)
+{
+    int rc = validate(B, H, W, C, skip_pixels);
+    if (rc) return rc;
+    PCNN_REQUIRE(bytes != nullptr, "hough: bytes is NULL");
+    const bool thr_mode = threshold_vote > 0;
+    Layout L = make_layout(B, H, W, C, skip_pixels, /*want_votes=*/thr_mode, thr_mode);
+    // + selection scratch of k_finalize
+    *bytes = L.total + align_up(sizeof(int) * ((size_t)B * PCNN_MAX_ROI + B + 1), 256);
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, const float* extents, const float* meta,
+                                   const float* gt, int B, int H, int W, int C, int num_gt, int num_meta, int is_train,
+                                   float inlier_threshold, int label_threshold, float threshold_vote,
+                                   float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
+                                   float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream)
+{
+    int rc = validate(B, H, W, C, skip_pixels);
+    if (rc) return rc;
+    PCNN_REQUIRE(is_train >= 0, "Need is_train >= 0, got %d", is_train);  // hough_voting_gpu_op.cc:309-311
+    PCNN_REQUIRE(num_meta >= 6, "hough: meta_data needs the intrinsics (num_meta >= 6, got %d)", num_meta);
+    PCNN_REQUIRE(num_gt == 0 || gt != nullptr, "hough: gt is NULL but num_gt = %d", num_gt);
+    PCNN_REQUIRE(label && vertex && extents && meta && top_box && top_pose && top_target && top_weight && top_domain &&
+                     num_rois && workspace, "hough: NULL tensor pointer");
+    const bool thr_mode = threshold_vote > 0;
+    size_t need = 0;
+    pcnn_hough_vote_workspace_bytes(B, H, W, C, skip_pixels, threshold_vote, &need);
+    if (workspace_bytes < need) {
+        set_error("hough: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return PCNN_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Layout L = make_layout(B, H, W, C, skip_pixels, thr_mode, thr_mode);
+    char* ws = (char*)workspace;
+    int* sel = (int*)(ws + L.total);
+    int* sel_n = sel + (size_t)B * PCNN_MAX_ROI;
+    ZeroList z;
+    const unsigned rows = PCNN_HOUGH_MAX_ROWS;
+    z.p[0] = top_box; z.n[0] = rows * 7;
+    z.p[1] = top_pose; z.n[1] = rows * 7;
+    z.p[2] = top_target; z.n[2] = rows * 4 * C;
+    z.p[3] = top_weight; z.n[3] = rows * 4 * C;
+    z.p[4] = reinterpret_cast<float*>(top_domain); z.n[4] = rows;
+    if (status) cudaMemsetAsync(status, 0, 4 * sizeof(int), st);
+    float* votes = thr_mode ? (float*)(ws + L.votes) : nullptr;
+    rc = run_front(L, ws, label, vertex, extents, meta, B, H, W, C, num_meta, inlier_threshold, label_threshold,
+                   skip_pixels, z, votes, st);
+    if (rc) return rc;
+    int* img_count = (int*)(ws + L.img_count);
+    int* slot_cls = (int*)(ws + L.slot_cls);
+    int* bbox = (int*)(ws + L.bbox);
+    int* cand_key = (int*)(ws + L.cand_key);
+    int* cand_val = (int*)(ws + L.cand_val);
+    int* cand_n = (int*)(ws + L.cand_n);
+    float4* cand_data = (float4*)(ws + L.cand_data);
+    const int cap = PCNN_MAX_ROI / B;  // .cu.cc:733
+    if (!thr_mode) {
+        k_select<<<B, 32, 0, st>>>(C, H * W, L.R, L.nbands, cap, L.cand_cap, img_count, slot_cls, bbox,
+                                   (const int2*)(ws + L.band_res), cand_key, cand_val, cand_n);
+    } else {
+        dim3 g((H * W + kThreads - 1) / kThreads, C - 1, B);
+        k_localmax<<<g, kThreads, 0, st>>>(H, W, C, L.R, threshold_vote, L.cand_cap, img_count, slot_cls, bbox, votes,
+                                           cand_key, cand_val, cand_n, status);
+    }
+    k_celldata<<<kNumSMs, kThreads, 0, st>>>(B, H, W, C, num_meta, inlier_threshold, L.cand_cap, extents, meta, slot_cls,
+                                             (const int*)(ws + L.cls_nsamp), (const int*)(ws + L.cls_soff),
+                                             (const Sample*)(ws + L.samples), L.samp_cap, cand_key, cand_n, cand_data);
+    k_finalize<<<1, kThreads, 0, st>>>(B, H, W, C, num_meta, num_gt, is_train, cap, L.cand_cap, thr_mode ? 1 : 0,
+                                       threshold_percentage, extents, meta, gt, slot_cls, cand_key, cand_val, cand_n,
+                                       cand_data, sel, sel_n, top_box, top_pose, top_target, top_weight, top_domain,
+                                       num_rois, status);
+    return check_launch("hough back kernels");
+}
+
+extern "C" int pcnn_hough_vote_planes(const int32_t* label, const float* vertex, const float* extents, const float* meta,
+                                      int B, int H, int W, int C, int num_meta, float inlier_threshold,
+                                      int label_threshold, int skip_pixels, float* votes, void* workspace,
+                                      size_t workspace_bytes, void* stream)
+{
+    int rc = validate(B, H, W, C, skip_pixels);
+    if (rc) return rc;
+    PCNN_REQUIRE(label && vertex && extents && meta && votes && workspace, "hough planes: NULL tensor pointer");
+    Layout L = make_layout(B, H, W, C, skip_pixels, false, false);
+    if (workspace_bytes < L.total) {
+        set_error("hough planes: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+        return PCNN_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(votes, 0, sizeof(float) * (size_t)B * C * H * W, st);
+    ZeroList z;
+    for (int k = 0; k < 5; k++) { z.p[k] = nullptr; z.n[k] = 0; }
+    return run_front(L, (char*)workspace, label, vertex, extents, meta, B, H, W, C, num_meta, inlier_threshold,
+                     label_threshold, skip_pixels, z, votes, st);
+}
+
+extern "C" int pcnn_hough_vote_bwd(float* grad_label, float* grad_vertex, int B, int H, int W, int C, void* stream)
+{
+    PCNN_REQUIRE(grad_label && grad_vertex, "hough bwd: NULL pointer");
+    size_t na = (size_t)B * H * W, nb = na * 3 * C;
+    k_zero2<<<4 * kNumSMs, 256, 0, (cudaStream_t)stream>>>(grad_label, na, grad_vertex, nb);
+    return check_launch("hough bwd");
+}

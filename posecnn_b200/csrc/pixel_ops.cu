@@ -1,0 +1,509 @@
+// pixel_ops.cu — RoiPool, Hardlabel, Project / Backproject and their gradients for sm_100a.
+//
+// All of these are HBM-bound gathers / streams; the kernels keep the
+// channel dimension (NHWC innermost) on adjacent lanes with 128-bit accesses, compute each
+// geometric quantity once per (pixel|voxel|bin) group of lanes, and size grids from the
+// element count (grid-stride loops, 148 SMs x resident CTAs).
+//
+// Behavioural specs (paths relative to /root/reference/lib):
+//   RoiPool fwd/bwd  roi_pooling_layer/roi_pooling_op_gpu.cu.cc:19-101, 134-229
+//   Hardlabel        hard_label_layer/hard_label_op_gpu.cu.cc:16-29, 54-63
+//   Project          projecting_layer/projecting_op_gpu.cu.cc:16-73, 101-169
+//   Backproject      backprojecting_layer/backprojecting_op_gpu.cu.cc:16-126, 158-217
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pcnn {
+
+static inline int grid_for(size_t work_items, int threads, int max_waves = 16)
+{
+    size_t blocks = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)kNumSMs * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ----------------------------------------------------------------------------------------
+// RoiPool forward: one thread per (roi, ph, pw, 4 channels)
+// ----------------------------------------------------------------------------------------
+struct RoiBin {
+    int b, cls, hs, he, ws, we;
+};
+
+__device__ __forceinline__ RoiBin roi_bin(const float* __restrict__ r, int ph, int pw, int ph_n, int pw_n, float scale,
+                                          int height, int width)
+{
+    RoiBin o;
+    o.b = (int)r[0];
+    o.cls = (int)r[1];
+    int rsw = (int)roundf(__fmul_rn(r[2], scale)), rsh = (int)roundf(__fmul_rn(r[3], scale));
+    int rew = (int)roundf(__fmul_rn(r[4], scale)), reh = (int)roundf(__fmul_rn(r[5], scale));
+    int rw = max(rew - rsw + 1, 1), rh = max(reh - rsh + 1, 1);
+    float bh = __fdiv_rn((float)rh, (float)ph_n), bw = __fdiv_rn((float)rw, (float)pw_n);
+    int hs = (int)floorf(__fmul_rn((float)ph, bh)), wsx = (int)floorf(__fmul_rn((float)pw, bw));
+    int he = (int)ceilf(__fmul_rn((float)(ph + 1), bh)), we = (int)ceilf(__fmul_rn((float)(pw + 1), bw));
+    o.hs = min(max(hs + rsh, 0), height);
+    o.he = min(max(he + rsh, 0), height);
+    o.ws = min(max(wsx + rsw, 0), width);
+    o.we = min(max(we + rsw, 0), width);
+    return o;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_roi_pool_fwd(const float* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois, int batch,
+               int height, int width, int channels, int ph_n, int pw_n, float scale, float* __restrict__ top,
+               int* __restrict__ argmax)
+{
+    const int cg = channels / VEC;
+    const size_t total = (size_t)num_rois * ph_n * pw_n * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(idx % cg);
+        size_t r1 = idx / cg;
+        int pw = (int)(r1 % pw_n);
+        r1 /= pw_n;
+        int ph = (int)(r1 % ph_n);
+        int n = (int)(r1 / ph_n);
+        RoiBin rb = roi_bin(rois + (size_t)n * channel_rois, ph, pw, ph_n, pw_n, scale, height, width);
+        bool empty = (rb.he <= rb.hs) || (rb.we <= rb.ws) || rb.b < 0 || rb.b >= batch;
+        float mv[VEC];
+        int mi[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { mv[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
+        if (!empty) {
+            const float* img = bottom + (size_t)rb.b * height * width * channels;
+            for (int h = rb.hs; h < rb.he; h++)
+                for (int w = rb.ws; w < rb.we; w++) {
+                    int bi = (h * width + w) * channels + g * VEC;
+                    float v[VEC];
+                    if (VEC == 4) {
+                        float4 q = __ldg(reinterpret_cast<const float4*>(img + bi));
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    } else {
+                        v[0] = __ldg(img + bi);
+                    }
+#pragma unroll
+                    for (int k = 0; k < VEC; k++)
+                        if (v[k] > mv[k]) { mv[k] = v[k]; mi[k] = bi + k; }
+                }
+        }
+        size_t o = ((size_t)(n * ph_n + ph) * pw_n + pw) * channels + g * VEC;
+        if (VEC == 4) {
+            *reinterpret_cast<float4*>(top + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+            *reinterpret_cast<int4*>(argmax + o) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+        } else {
+            top[o] = mv[0];
+            argmax[o] = mi[0];
+        }
+    }
+}
+
+// pool_channel mode: one output channel = channel roi_cls of the input (.cu.cc:84-87)
+__global__ void __launch_bounds__(256)
+k_roi_pool_fwd_cls(const float* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois,
+                   int batch, int height, int width, int channels, int ph_n, int pw_n, float scale,
+                   float* __restrict__ top, int* __restrict__ argmax)
+{
+    const int total = num_rois * ph_n * pw_n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int pw = idx % pw_n, ph = (idx / pw_n) % ph_n, n = idx / (pw_n * ph_n);
+        RoiBin rb = roi_bin(rois + (size_t)n * channel_rois, ph, pw, ph_n, pw_n, scale, height, width);
+        bool empty = (rb.he <= rb.hs) || (rb.we <= rb.ws) || rb.b < 0 || rb.b >= batch || rb.cls < 0 || rb.cls >= channels;
+        float mv = empty ? 0.f : -FLT_MAX;
+        int mi = -1;
+        if (!empty) {
+            const float* img = bottom + (size_t)rb.b * height * width * channels;
+            for (int h = rb.hs; h < rb.he; h++)
+                for (int w = rb.ws; w < rb.we; w++) {
+                    int bi = (h * width + w) * channels + rb.cls;
+                    float v = __ldg(img + bi);
+                    if (v > mv) { mv = v; mi = bi; }
+                }
+        }
+        top[idx] = mv;
+        argmax[idx] = mi;
+    }
+}
+
+// RoiPool backward as a scatter through argmax: grad_in[b, argmax] += top_diff.  The
+// reference gathers per input element over ALL rois (.cu.cc:153); the set of (bin, element)
+// pairs that contribute is identical: a bin contributes to an element iff its argmax is that
+// element (the feasibility tests of .cu.cc:169-204 are implied by how argmax was produced).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_roi_pool_bwd(const float* __restrict__ top_diff, const int* __restrict__ argmax, const float* __restrict__ rois,
+               int batch, int num_rois, int channel_rois, int height, int width, int channels, int out_ch, int bins,
+               float* __restrict__ bottom_diff)
+{
+    const int cg = out_ch / VEC;
+    const size_t total = (size_t)num_rois * bins * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        size_t e = idx * VEC;
+        int n = (int)(e / ((size_t)bins * out_ch));
+        int b = (int)rois[(size_t)n * channel_rois];
+        if (b < 0 || b >= batch) continue;
+        float* img = bottom_diff + (size_t)b * height * width * channels;
+        if (VEC == 4) {
+            int4 a = *reinterpret_cast<const int4*>(argmax + e);
+            float4 g = *reinterpret_cast<const float4*>(top_diff + e);
+            if (a.x >= 0) atomicAdd(img + a.x, g.x);
+            if (a.y >= 0) atomicAdd(img + a.y, g.y);
+            if (a.z >= 0) atomicAdd(img + a.z, g.z);
+            if (a.w >= 0) atomicAdd(img + a.w, g.w);
+        } else {
+            int a = argmax[e];
+            if (a >= 0) atomicAdd(img + a, top_diff[e]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_zero(float* __restrict__ p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, g = (size_t)gridDim.x * blockDim.x;
+    size_t n4 = n / 4;
+    for (size_t k = i; k < n4; k += g) st_stream_f4(reinterpret_cast<float4*>(p) + k, make_float4(0, 0, 0, 0));
+    for (size_t k = n4 * 4 + i; k < n; k += g) p[k] = 0.f;
+}
+
+// ----------------------------------------------------------------------------------------
+// Hardlabel: streaming one-hot writer.  out[p,:] = 0; out[p,g] = 1 iff g != -1 and
+// (g > 0 or prob[p,g] < threshold).  Labels outside [-1, C) write nothing (the reference
+// would write out of bounds there).
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_hard_label(const float* __restrict__ prob, const int* __restrict__ gt, size_t npix, int C, float threshold,
+             float* __restrict__ top)
+{
+    const size_t total = npix * C;
+    const size_t n4 = total / 4;
+    const size_t g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = g0; k < n4; k += gs) {
+        size_t e = k * 4;
+        size_t p = e / C;
+        int ch = (int)(e % C);
+        float v[4];
+        int g = gt[p];
+        bool hot = g >= 0 && g < C && (g > 0 || __ldg(prob + p * C) < threshold);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = (hot && ch == g) ? 1.f : 0.f;
+            if (++ch == C) {
+                ch = 0;
+                p++;
+                if (j < 3 && p < npix) {
+                    g = gt[p];
+                    hot = g >= 0 && g < C && (g > 0 || __ldg(prob + p * C) < threshold);
+                }
+            }
+        }
+        st_stream_f4(reinterpret_cast<float4*>(top) + k, make_float4(v[0], v[1], v[2], v[3]));
+    }
+    for (size_t e = n4 * 4 + g0; e < total; e += gs) {
+        size_t p = e / C;
+        int ch = (int)(e % C);
+        int g = gt[p];
+        bool hot = g >= 0 && g < C && (g > 0 || prob[p * C] < threshold);
+        top[e] = (hot && ch == g) ? 1.f : 0.f;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Project / Backproject geometry (same rounding as nvcc gives the reference expressions)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pixel_to_voxel(const float* __restrict__ m, int w, int h, float depth, int G, int& vd,
+                                               int& vh, int& vw)
+{
+    float fw = (float)w, fh = (float)h;
+    float RX = __fadd_rn(__fmaf_rn(m[9], fw, __fmul_rn(m[10], fh)), m[11]);
+    float RY = __fadd_rn(__fmaf_rn(m[12], fw, __fmul_rn(m[13], fh)), m[14]);
+    float RZ = __fadd_rn(__fmaf_rn(m[15], fw, __fmul_rn(m[16], fh)), m[17]);
+    float X = __fmul_rn(depth, RX), Y = __fmul_rn(depth, RY), Z = __fmul_rn(depth, RZ);
+    float X1 = __fadd_rn(__fmaf_rn(m[32], Z, __fmaf_rn(m[30], X, __fmul_rn(m[31], Y))), m[33]);
+    float Y1 = __fadd_rn(__fmaf_rn(m[36], Z, __fmaf_rn(m[34], X, __fmul_rn(m[35], Y))), m[37]);
+    float Z1 = __fadd_rn(__fmaf_rn(m[40], Z, __fmaf_rn(m[38], X, __fmul_rn(m[39], Y))), m[41]);
+    vd = (int)roundf(__fdiv_rn(__fsub_rn(X1, m[45]), m[42]));
+    vh = (int)roundf(__fdiv_rn(__fsub_rn(Y1, m[46]), m[43]));
+    vw = (int)roundf(__fdiv_rn(__fsub_rn(Z1, m[47]), m[44]));
+    return vd >= 0 && vd < G && vh >= 0 && vh < G && vw >= 0 && vw < G;
+}
+
+__device__ __forceinline__ void voxel_to_pixel(const float* __restrict__ m, int d, int h, int w, int& px, int& py,
+                                               float& Z1)
+{
+    float X = __fmaf_rn((float)d, m[42], m[45]);
+    float Y = __fmaf_rn((float)h, m[43], m[46]);
+    float Z = __fmaf_rn((float)w, m[44], m[47]);
+    float X1 = __fadd_rn(__fmaf_rn(m[20], Z, __fmaf_rn(m[18], X, __fmul_rn(m[19], Y))), m[21]);
+    float Y1 = __fadd_rn(__fmaf_rn(m[24], Z, __fmaf_rn(m[22], X, __fmul_rn(m[23], Y))), m[25]);
+    Z1 = __fadd_rn(__fmaf_rn(m[28], Z, __fmaf_rn(m[26], X, __fmul_rn(m[27], Y))), m[29]);
+    float x1 = __fmaf_rn(m[2], Z1, __fmaf_rn(m[0], X1, __fmul_rn(m[1], Y1)));
+    float x2 = __fmaf_rn(m[5], Z1, __fmaf_rn(m[3], X1, __fmul_rn(m[4], Y1)));
+    float x3 = __fmaf_rn(m[8], Z1, __fmaf_rn(m[6], X1, __fmul_rn(m[7], Y1)));
+    float a = __fdiv_rn(x1, x3), b = __fdiv_rn(x2, x3);
+    // clamp before the int conversion so that inf / NaN cannot produce a bogus in-range pixel
+    a = fminf(fmaxf(a, -1e8f), 1e8f);
+    b = fminf(fmaxf(b, -1e8f), 1e8f);
+    px = (a == a) ? (int)roundf(a) : -0x40000000;
+    py = (b == b) ? (int)roundf(b) : -0x40000000;
+}
+
+// out[B,H,W,Cf] = vox[B,G,G,G,Cf] at the voxel hit by each pixel, else 0
+// (ProjectForward .cu.cc:16-73; BackprojectBackward .cu.cc:158-217)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_pixel_gather(const float* __restrict__ vox, const float* __restrict__ depth, const float* __restrict__ meta, int B,
+               int H, int W, int Cf, int num_meta, int G, float* __restrict__ out)
+{
+    const int cg = Cf / VEC;
+    const size_t total = (size_t)B * H * W * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(idx % cg);
+        size_t pix = idx / cg;
+        int w = (int)(pix % W);
+        int h = (int)((pix / W) % H);
+        int n = (int)(pix / ((size_t)W * H));
+        int vd, vh, vw;
+        bool inside = pixel_to_voxel(meta + (size_t)n * num_meta, w, h, __ldg(depth + pix), G, vd, vh, vw);
+        if (VEC == 4) {
+            float4 v = make_float4(0, 0, 0, 0);
+            if (inside) v = __ldg(reinterpret_cast<const float4*>(vox + ((((size_t)n * G + vd) * G + vh) * G + vw) * Cf) + g);
+            st_stream_f4(reinterpret_cast<float4*>(out + pix * Cf) + g, v);
+        } else {
+            out[pix * Cf + g] = inside ? __ldg(vox + ((((size_t)n * G + vd) * G + vh) * G + vw) * Cf + g) : 0.f;
+        }
+    }
+}
+
+// window average of a [B,H,W,nch] map into a [B,G,G,G,nch] grid
+// (BackprojectForward .cu.cc:16-126 for data (+flag) and labels (+label_3d fallback);
+//  ProjectBackward .cu.cc:101-169 for top_diff)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_voxel_average(const float* __restrict__ src, const float* __restrict__ depth, const float* __restrict__ meta,
+                const float* __restrict__ fallback, int B, int H, int W, int nch, int num_meta, int G, int ks,
+                float threshold, float* __restrict__ dst, float* __restrict__ flag)
+{
+    const int cg = nch / VEC;
+    const size_t total = (size_t)B * G * G * G * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(idx % cg);
+        size_t vox = idx / cg;
+        int w = (int)(vox % G);
+        int h = (int)((vox / G) % G);
+        int d = (int)((vox / ((size_t)G * G)) % G);
+        int n = (int)(vox / ((size_t)G * G * G));
+        int px, py;
+        float Z1;
+        voxel_to_pixel(meta + (size_t)n * num_meta, d, h, w, px, py, Z1);
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[k] = 0.f;
+        int count = 0;
+        const int x0 = max(px - ks, 0), x1 = min(px + ks, W - 1);
+        const int y0 = max(py - ks, 0), y1 = min(py + ks, H - 1);
+        for (int x = x0; x <= x1; x++)
+            for (int y = y0; y <= y1; y++) {
+                size_t pix = ((size_t)n * H + y) * W + x;
+                float dep = __ldg(depth + pix);
+                if (fabsf(__fsub_rn(dep, Z1)) < threshold) {
+                    count++;
+                    if (VEC == 4) {
+                        float4 q = __ldg(reinterpret_cast<const float4*>(src + pix * nch) + g);
+                        acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+                    } else {
+                        acc[0] += __ldg(src + pix * nch + g);
+                    }
+                }
+            }
+        float fl = 0.f;
+        if (count == 0) {
+            if (fallback) {
+                if (VEC == 4) {
+                    float4 q = __ldg(reinterpret_cast<const float4*>(fallback + vox * nch) + g);
+                    acc[0] = q.x; acc[1] = q.y; acc[2] = q.z; acc[3] = q.w;
+                } else {
+                    acc[0] = __ldg(fallback + vox * nch + g);
+                }
+            }
+        } else {
+            float cf = (float)count;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[k] = __fdiv_rn(acc[k], cf);
+            fl = 1.f;
+        }
+        if (VEC == 4) {
+            st_stream_f4(reinterpret_cast<float4*>(dst + vox * nch) + g, make_float4(acc[0], acc[1], acc[2], acc[3]));
+            if (flag) st_stream_f4(reinterpret_cast<float4*>(flag + vox * nch) + g, make_float4(fl, fl, fl, fl));
+        } else {
+            dst[vox * nch + g] = acc[0];
+            if (flag) flag[vox * nch + g] = fl;
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace pcnn
+
+using namespace pcnn;
+
+extern "C" int pcnn_roi_pool_fwd(const float* bottom, const float* rois, int num_rois, int channel_rois, int batch,
+                                 int height, int width, int channels, int pooled_height, int pooled_width,
+                                 float spatial_scale, int pool_channel, float* top, int32_t* argmax, void* stream)
+{
+    PCNN_REQUIRE(pooled_height >= 0, "Need pooled_height >= 0, got %d", pooled_height);  // roi_pooling_op.cc:286-288
+    PCNN_REQUIRE(pooled_width >= 0, "Need pooled_width >= 0, got %d", pooled_width);
+    PCNN_REQUIRE(channel_rois >= 6, "rois must have at least 6 columns [b, cls, x1, y1, x2, y2] (got %d)", channel_rois);
+    PCNN_REQUIRE(num_rois >= 0 && batch >= 1 && height >= 1 && width >= 1 && channels >= 1, "roi_pool: bad shape");
+    PCNN_REQUIRE(bottom && rois && top && argmax, "roi_pool: NULL tensor pointer");
+    if (num_rois == 0 || pooled_height == 0 || pooled_width == 0) return PCNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pool_channel) {
+        int total = num_rois * pooled_height * pooled_width;
+        k_roi_pool_fwd_cls<<<grid_for(total, 256), 256, 0, st>>>(bottom, rois, num_rois, channel_rois, batch, height, width,
+                                                                 channels, pooled_height, pooled_width, spatial_scale, top,
+                                                                 argmax);
+    } else if (channels % 4 == 0 && aligned16(bottom) && aligned16(top) && aligned16(argmax)) {
+        size_t total = (size_t)num_rois * pooled_height * pooled_width * (channels / 4);
+        k_roi_pool_fwd<4><<<grid_for(total, 256), 256, 0, st>>>(bottom, rois, num_rois, channel_rois, batch, height, width,
+                                                                channels, pooled_height, pooled_width, spatial_scale, top,
+                                                                argmax);
+    } else {
+        size_t total = (size_t)num_rois * pooled_height * pooled_width * channels;
+        k_roi_pool_fwd<1><<<grid_for(total, 256), 256, 0, st>>>(bottom, rois, num_rois, channel_rois, batch, height, width,
+                                                                channels, pooled_height, pooled_width, spatial_scale, top,
+                                                                argmax);
+    }
+    return check_launch("roi_pool_fwd");
+}
+
+extern "C" int pcnn_roi_pool_bwd(const float* top_diff, const int32_t* argmax, const float* rois, int batch,
+                                 int num_rois, int channel_rois, int height, int width, int channels,
+                                 int pooled_height, int pooled_width, float spatial_scale, int pool_channel,
+                                 float* bottom_diff, void* stream)
+{
+    (void)spatial_scale;
+    PCNN_REQUIRE(channel_rois >= 6, "rois must have at least 6 columns (got %d)", channel_rois);
+    PCNN_REQUIRE(top_diff && argmax && rois && bottom_diff, "roi_pool_grad: NULL tensor pointer");
+    PCNN_REQUIRE(batch >= 1 && height >= 1 && width >= 1 && channels >= 1 && num_rois >= 0, "roi_pool_grad: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n_in = (size_t)batch * height * width * channels;
+    k_fill_zero<<<grid_for(n_in / 4 + 1, 256), 256, 0, st>>>(bottom_diff, n_in);
+    int bins = pooled_height * pooled_width;
+    if (num_rois > 0 && bins > 0) {
+        int out_ch = pool_channel ? 1 : channels;
+        if (out_ch % 4 == 0 && aligned16(top_diff) && aligned16(argmax)) {
+            size_t total = (size_t)num_rois * bins * (out_ch / 4);
+            k_roi_pool_bwd<4><<<grid_for(total, 256), 256, 0, st>>>(top_diff, argmax, rois, batch, num_rois, channel_rois,
+                                                                    height, width, channels, out_ch, bins, bottom_diff);
+        } else {
+            size_t total = (size_t)num_rois * bins * out_ch;
+            k_roi_pool_bwd<1><<<grid_for(total, 256), 256, 0, st>>>(top_diff, argmax, rois, batch, num_rois, channel_rois,
+                                                                    height, width, channels, out_ch, bins, bottom_diff);
+        }
+    }
+    return check_launch("roi_pool_bwd");
+}
+
+extern "C" int pcnn_hard_label_fwd(const float* prob, const int32_t* gt, int B, int H, int W, int C, float threshold,
+                                   float* top, void* stream)
+{
+    PCNN_REQUIRE(prob && gt && top, "hard_label: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1, "hard_label: bad shape");
+    PCNN_REQUIRE(aligned16(top), "hard_label: output must be 16-byte aligned");
+    size_t npix = (size_t)B * H * W;
+    k_hard_label<<<grid_for(npix * C / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(prob, gt, npix, C, threshold, top);
+    return check_launch("hard_label_fwd");
+}
+
+extern "C" int pcnn_hard_label_bwd(int B, int H, int W, int C, float* grad_prob, float* grad_gt, void* stream)
+{
+    PCNN_REQUIRE(grad_prob && grad_gt, "hard_label_grad: NULL tensor pointer");
+    size_t npix = (size_t)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fill_zero<<<grid_for(npix * C / 4 + 1, 256), 256, 0, st>>>(grad_prob, npix * C);
+    k_fill_zero<<<grid_for(npix / 4 + 1, 256), 256, 0, st>>>(grad_gt, npix);
+    return check_launch("hard_label_bwd");
+}
+
+static int launch_gather(const float* vox, const float* depth, const float* meta, int B, int H, int W, int Cf,
+                         int num_meta, int G, float* out, cudaStream_t st)
+{
+    if (Cf % 4 == 0 && aligned16(vox) && aligned16(out)) {
+        size_t total = (size_t)B * H * W * (Cf / 4);
+        k_pixel_gather<4><<<grid_for(total, 256), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
+    } else {
+        size_t total = (size_t)B * H * W * Cf;
+        k_pixel_gather<1><<<grid_for(total, 256), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
+    }
+    return check_launch("pixel gather");
+}
+
+static int launch_average(const float* src, const float* depth, const float* meta, const float* fallback, int B, int H,
+                          int W, int nch, int num_meta, int G, int ks, float thr, float* dst, float* flag, cudaStream_t st)
+{
+    bool v4 = nch % 4 == 0 && aligned16(src) && aligned16(dst) && (!fallback || aligned16(fallback)) &&
+              (!flag || aligned16(flag));
+    if (v4) {
+        size_t total = (size_t)B * G * G * G * (nch / 4);
+        k_voxel_average<4><<<grid_for(total, 256), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G, ks,
+                                                                 thr, dst, flag);
+    } else {
+        size_t total = (size_t)B * G * G * G * nch;
+        k_voxel_average<1><<<grid_for(total, 256), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G, ks,
+                                                                 thr, dst, flag);
+    }
+    return check_launch("voxel average");
+}
+
+extern "C" int pcnn_backproject_fwd(const float* data, const float* label, const float* depth, const float* meta,
+                                    const float* label_3d, int B, int H, int W, int Cf, int C, int num_meta,
+                                    int grid_size, int kernel_size, float threshold, float* top_data,
+                                    float* top_label, float* top_flag, void* stream)
+{
+    PCNN_REQUIRE(grid_size >= 0, "Need grid_size >= 0, got %d", grid_size);        // backprojecting_op.cc:303-305
+    PCNN_REQUIRE(kernel_size >= 0, "Need kernel_size >= 0, got %d", kernel_size);  // :310-312
+    PCNN_REQUIRE(threshold >= 0, "Need threshold >= 0, got %f", threshold);        // :317-319
+    PCNN_REQUIRE(num_meta >= 48, "backproject: meta_data needs 48 floats (got %d)", num_meta);
+    PCNN_REQUIRE(data && label && depth && meta && label_3d && top_data && top_label && top_flag,
+                 "backproject: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cf >= 1 && C >= 1, "backproject: bad shape");
+    if (grid_size == 0) return PCNN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_average(data, depth, meta, nullptr, B, H, W, Cf, num_meta, grid_size, kernel_size, threshold, top_data,
+                            top_flag, st);
+    if (rc) return rc;
+    return launch_average(label, depth, meta, label_3d, B, H, W, C, num_meta, grid_size, kernel_size, threshold, top_label,
+                          nullptr, st);
+}
+
+extern "C" int pcnn_backproject_bwd(const float* top_diff, const float* depth, const float* meta, int B, int H, int W,
+                                    int Cf, int num_meta, int grid_size, float* bottom_diff, void* stream)
+{
+    PCNN_REQUIRE(top_diff && depth && meta && bottom_diff, "backproject_grad: NULL tensor pointer");
+    PCNN_REQUIRE(num_meta >= 48 && grid_size >= 1, "backproject_grad: bad meta/grid");
+    return launch_gather(top_diff, depth, meta, B, H, W, Cf, num_meta, grid_size, bottom_diff, (cudaStream_t)stream);
+}
+
+extern "C" int pcnn_project_fwd(const float* data, const float* depth, const float* meta, int B, int H, int W, int Cf,
+                                int num_meta, int grid_size, float* top, void* stream)
+{
+    PCNN_REQUIRE(data && depth && meta && top, "project: NULL tensor pointer");
+    PCNN_REQUIRE(num_meta >= 48 && grid_size >= 1, "project: bad meta/grid");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cf >= 1, "project: bad shape");
+    return launch_gather(data, depth, meta, B, H, W, Cf, num_meta, grid_size, top, (cudaStream_t)stream);
+}
+
+extern "C" int pcnn_project_bwd(const float* top_diff, const float* depth, const float* meta, int B, int H, int W,
+                                int Cf, int num_meta, int grid_size, int kernel_size, float threshold,
+                                float* bottom_diff, void* stream)
+{
+    PCNN_REQUIRE(top_diff && depth && meta && bottom_diff, "project_grad: NULL tensor pointer");
+    PCNN_REQUIRE(kernel_size >= 0, "Need kernel_size >= 0, got %d", kernel_size);  // projecting_op.cc:226-228
+    PCNN_REQUIRE(threshold >= 0, "Need threshold >= 0, got %f", threshold);
+    PCNN_REQUIRE(num_meta >= 48 && grid_size >= 1, "project_grad: bad meta/grid");
+    return launch_average(top_diff, depth, meta, nullptr, B, H, W, Cf, num_meta, grid_size, kernel_size, threshold,
+                          bottom_diff, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,52 @@
+"""Input definitions shared by the golden-vector generator (make_golden.py, runs the reference's
+own CUDA kernels on the GPU box) and the tests that consume tests/golden/*.npz.  Inputs are
+regenerated from seeds; only outputs are stored."""
+import numpy as np
+
+from posecnn_b200 import synth
+
+HOUGH_CASES = {
+    # name: (scene kwargs, is_train, vote_thr, per_thr, skip)
+    "h_test_a": (dict(batch=2, height=120, width=160, num_classes=5, objects_per_image=3, seed=3, min_pixels=520), 0, -1.0, 0.02, 10),
+    "h_train_b": (dict(batch=2, height=120, width=160, num_classes=6, objects_per_image=3, seed=7, min_pixels=520), 1, -1.0, 0.02, 10),
+    "h_thr_c": (dict(batch=2, height=120, width=160, num_classes=5, objects_per_image=3, seed=13, min_pixels=520, dir_noise=0.1), 0, 20.0, 0.002, 10),
+    "h_skip1_d": (dict(batch=1, height=96, width=128, num_classes=4, objects_per_image=2, seed=17, min_pixels=520), 0, -1.0, 0.02, 1),
+    "h_full_e": (dict(batch=1, height=480, width=640, num_classes=22, seed=1234), 0, -1.0, 0.02, 10),
+}
+
+
+def hough_inputs(name):
+    kw, is_train, vt, pt, skip = HOUGH_CASES[name]
+    return synth.make_scene(**kw), is_train, vt, pt, skip
+
+
+def roi_inputs():
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((3, 30, 40, 32)).astype(np.float32)
+    rois = synth.make_rois(17, 3, num_classes=22, seed=2)
+    rois[3, 2:6] = [700, 500, 710, 505]
+    rois[4, 2:6] = [100, 100, 90, 80]
+    grad = rng.standard_normal((17, 7, 7, 32)).astype(np.float32)
+    return data, rois, grad
+
+
+def hard_label_inputs():
+    rng = np.random.default_rng(2)
+    return rng.random((2, 37, 53, 22)).astype(np.float32), rng.integers(-1, 22, (2, 37, 53)).astype(np.int32)
+
+
+def projection_inputs():
+    case = synth.make_projection_case(2, 48, 64, 8, 3, 16, seed=5)
+    rng = np.random.default_rng(6)
+    case["g3"] = rng.standard_normal((2, 16, 16, 16, 8)).astype(np.float32)
+    case["g2"] = rng.standard_normal((2, 48, 64, 8)).astype(np.float32)
+    return case
+
+
+def avgdist_inputs():
+    pts = synth.make_model_points(22, 300)
+    pred, targ, wt = synth.make_pose_batch(9, 22, seed=9)
+    pred[0] = 0; targ[0] = 0; wt[0] = 0
+    q = np.array([0.8, 0.2, -0.4, 0.4], np.float32); p = q + np.array([0.1, -0.05, 0.02, 0.07], np.float32)
+    targ[0, 64:68] = q / np.linalg.norm(q); pred[0, 64:68] = p / np.linalg.norm(p); wt[0, 64:68] = 1
+    return pred, targ, wt, pts, synth.LOV_SYMMETRY.copy()

@@ -1,0 +1,194 @@
+"""CPU-only tests (-m "not gpu"): the oracle's own properties, the host-side op modules and
+the C ABI surface (library loads, every symbol declared in include/posecnn_b200.h is exported).
+No compute call is made without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from posecnn_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(native_lib):
+    hdr = open(os.path.join(ROOT, "include", "posecnn_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(pcnn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(native_lib, n), f"{n} declared in include/posecnn_b200.h but not exported"
+    assert native_lib.pcnn_version() >= 100
+
+
+def test_abi_argument_validation_without_gpu(native_lib):
+    # validation happens before any CUDA call, so these are safe on a CPU-only box
+    nbytes = ctypes.c_size_t(0)
+    assert native_lib.pcnn_hough_vote_workspace_bytes(1, 480, 640, 22, 10, ctypes.c_float(-1.0), ctypes.byref(nbytes)) == 0
+    assert nbytes.value > 0
+    small = nbytes.value
+    assert native_lib.pcnn_hough_vote_workspace_bytes(32, 480, 640, 22, 10, ctypes.c_float(-1.0), ctypes.byref(nbytes)) == 0
+    assert nbytes.value > small
+    assert native_lib.pcnn_hough_vote_workspace_bytes(1, 480, 640, 1, 10, ctypes.c_float(-1.0), ctypes.byref(nbytes)) == -1
+    native_lib.pcnn_last_error.restype = ctypes.c_char_p
+    assert b"C >= 2" in native_lib.pcnn_last_error()
+    assert native_lib.pcnn_hough_vote_workspace_bytes(1, 480, 640, 22, 0, ctypes.c_float(-1.0), ctypes.byref(nbytes)) == -1
+    assert native_lib.pcnn_roi_pool_fwd(None, None, 1, 5, 1, 4, 4, 4, 7, 7, ctypes.c_float(1.0), 0, None, None, None) == -1
+
+
+def test_ops_refuse_cpu_tensors(native_lib):
+    import torch
+    from posecnn_b200.hard_label_layer import hard_label_op
+    from posecnn_b200.roi_pooling_layer import roi_pooling_op
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        hard_label_op.hard_label(torch.zeros(1, 2, 2, 3), torch.zeros(1, 2, 2, dtype=torch.int32), 1.0)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        roi_pooling_op.roi_pool(torch.zeros(1, 4, 4, 4), torch.zeros(1, 7), 7, 7, 1.0, 0)
+
+
+def test_reference_style_imports():
+    """lib/networks/network.py:6-26 imports `<layer>.<layer>_op`; with posecnn_b200/ on sys.path
+    the same statements resolve to this package."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import hough_voting_gpu_layer.hough_voting_gpu_op as h, roi_pooling_layer.roi_pooling_op as r,"
+            "hard_label_layer.hard_label_op as hl, backprojecting_layer.backprojecting_op as b,"
+            "projecting_layer.projecting_op as p, average_distance_loss.average_distance_loss_op as a;"
+            "assert all(hasattr(m, n) for m, n in [(h,'hough_voting_gpu'),(h,'hough_voting_gpu_grad'),(r,'roi_pool'),"
+            "(r,'roi_pool_grad'),(hl,'hard_label'),(hl,'hard_label_grad'),(b,'backproject'),(b,'backproject_grad'),"
+            "(p,'project'),(p,'project_grad'),(a,'average_distance_loss'),(a,'average_distance_loss_grad')])"
+            % (ROOT, os.path.join(ROOT, "posecnn_b200")))
+    subprocess.check_call([sys.executable, "-c", code])
+
+
+def test_oracle_hough_recovers_planted_centres():
+    sc = synth.make_scene(batch=2, height=120, width=160, num_classes=5, objects_per_image=2, seed=11,
+                          dir_noise=0.0, min_pixels=520)
+    outs, dbg = oracle.hough_voting_gpu(sc["label"], sc["vertex"], sc["extents"], sc["meta"], sc["gt"], 0, -1.0, 0.02, 10,
+                                        debug=True)
+    box, pose = outs[0], outs[1]
+    found = {(int(r[0]), int(r[1])): r for r in box}
+    assert dbg["num_rois"] == len(found) >= 2
+    K = synth.intrinsics(120, 160)
+    for (b, cls, cx, cy, z) in sc["centers"]:
+        if (sc["label"][b] == cls).sum() <= 500:
+            continue
+        r = found[(b, cls)]
+        x, y = 0.5 * (r[2] + r[4]), 0.5 * (r[3] + r[5])
+        assert abs(x - cx) <= 3 and abs(y - cy) <= 3        # >= 3 px tolerance for the cone vote
+        row = [i for i in range(box.shape[0]) if int(box[i, 0]) == b and int(box[i, 1]) == cls][0]
+        assert abs(pose[row, 6] - z) < 0.02 * z
+        assert abs(pose[row, 4] - z * (x - K[0, 2]) / K[0, 0]) < 1e-3
+
+
+def test_oracle_hough_dummy_row_and_cap():
+    sc = synth.make_scene(batch=1, height=60, width=80, num_classes=3, objects_per_image=1, seed=2, min_pixels=100)
+    # every object is below the 500-pixel label threshold -> dummy zero row (hough_voting_gpu_op.cc:379-383)
+    outs = oracle.hough_voting_gpu(sc["label"], sc["vertex"], sc["extents"], sc["meta"], sc["gt"], 0, -1.0, 0.02, 10)
+    assert outs[0].shape == (1, 7) and not outs[0].any()
+    # batch 64 -> cap = 128 / 64 = 2 maxima per image (SURVEY finding 3)
+    sc = synth.make_scene(batch=1, height=120, width=160, num_classes=6, objects_per_image=4, seed=5, min_pixels=520)
+    lab = np.repeat(sc["label"], 64, 0)[:64]
+    cnt = sum((sc["label"][0] == c).sum() > 500 for c in range(1, 6))
+    assert cnt >= 3
+    outs, dbg = oracle.hough_voting_gpu(lab[:64], np.repeat(sc["vertex"], 64, 0), sc["extents"], np.repeat(sc["meta"], 64, 0),
+                                        sc["gt"], 0, -1.0, 0.02, 10, debug=False), None
+    box = outs[0]
+    assert box.shape[0] == 64 * 2
+    assert np.bincount(box[:, 0].astype(int)).tolist() == [2] * 64
+
+
+def test_oracle_hough_train_rows():
+    sc = synth.make_scene(batch=1, height=120, width=160, num_classes=4, objects_per_image=2, seed=3, min_pixels=520)
+    outs = oracle.hough_voting_gpu(sc["label"], sc["vertex"], sc["extents"], sc["meta"], sc["gt"], 1, -1.0, 0.02, 10)
+    box, pose, target, weight, domain = outs
+    assert box.shape[0] % 9 == 0 and box.shape[0] >= 9
+    for g in range(box.shape[0] // 9):
+        base = box[9 * g]
+        ww, hh = base[4] - base[2], base[5] - base[3]
+        for j in range(1, 9):
+            r = box[9 * g + j]
+            assert r[0] == base[0] and r[1] == base[1] and r[6] == base[6]
+            np.testing.assert_allclose([r[4] - r[2], r[5] - r[3]], [ww, hh], rtol=1e-5)
+            assert abs(abs(r[2] - base[2]) / ww - 0.05) < 1e-4 or r[2] == base[2]
+        np.testing.assert_array_equal(pose[9 * g:9 * g + 9], np.repeat(pose[9 * g:9 * g + 1], 9, 0))
+        cls = int(base[1])
+        # the synthetic gt pose projects onto the planted ellipse -> IoU > 0.2 -> target = gt quaternion
+        gt_row = [r for r in sc["gt"] if int(r[1]) == cls][0]
+        np.testing.assert_allclose(target[9 * g, 4 * cls:4 * cls + 4], gt_row[6:10])
+        assert weight[9 * g:9 * g + 9, 4 * cls:4 * cls + 4].all() and weight.sum() <= box.shape[0] * 4
+    assert not domain.any()
+    outs0 = oracle.hough_voting_gpu(sc["label"], sc["vertex"], sc["extents"], sc["meta"], None, 1, -1.0, 0.02, 10)
+    assert outs0[4].all() and not outs0[3].any()      # num_gt == 0 -> domain flag 1 (.cu.cc:433-436)
+
+
+def test_oracle_roi_pool_properties():
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((2, 12, 16, 8)).astype(np.float32)
+    rois = synth.make_rois(6, 2, height=96, width=128, num_classes=5, seed=1)
+    top, arg = oracle.roi_pool(data, rois, 7, 7, 1.0 / 8.0)
+    assert top.shape == (6, 7, 7, 8) and arg.dtype == np.int32
+    flat = data.reshape(2, -1)
+    for n in range(6):
+        b = int(rois[n, 0])
+        m = arg[n] >= 0
+        np.testing.assert_array_equal(top[n][m], flat[b][arg[n][m]])     # value at argmax
+        assert (top[n][~m] == 0).all()                                   # empty bins -> 0, argmax -1
+        assert ((arg[n][m] % 8) == np.broadcast_to(np.arange(8), arg[n].shape)[m]).all()  # channel preserved
+    g = rng.standard_normal(top.shape).astype(np.float32)
+    gin = oracle.roi_pool_grad(data, rois, arg, g, 7, 7, 1.0 / 8.0)
+    np.testing.assert_allclose(gin.sum(), g[arg >= 0].sum(), rtol=1e-4)  # every pooled gradient lands somewhere
+
+
+def test_oracle_hard_label():
+    rng = np.random.default_rng(1)
+    prob = rng.random((1, 5, 7, 4)).astype(np.float32)
+    gt = rng.integers(-1, 4, (1, 5, 7)).astype(np.int32)
+    out = oracle.hard_label(prob, gt, 0.5)
+    assert set(np.unique(out)) <= {0.0, 1.0} and (out.sum(-1) <= 1).all()
+    exp = np.zeros_like(prob)
+    for idx in np.ndindex(1, 5, 7):
+        g = gt[idx]
+        if g != -1 and (g > 0 or prob[idx][g] < 0.5):
+            exp[idx][g] = 1
+    np.testing.assert_array_equal(out, exp)
+    assert (oracle.hard_label(prob, gt, 1.0)[gt == 0][:, 0] == 1).all()   # threshold 1.0 (lov_color_2d.yml:26)
+
+
+def test_oracle_project_backproject_consistency():
+    case = synth.make_projection_case(1, 24, 32, 4, 3, 16, seed=4)
+    out, amb = oracle.project(case["vox"], case["depth"], case["meta"], return_ambig=True)
+    assert out.shape == (1, 24, 32, 4)
+    # every non-zero output pixel equals some voxel of the grid (gather), zeros where the ray leaves the grid
+    voxset = {tuple(np.round(v, 6)) for v in case["vox"].reshape(-1, 4)}
+    nz = out.reshape(-1, 4)[np.abs(out.reshape(-1, 4)).sum(1) > 0]
+    assert len(nz) > 100 and all(tuple(np.round(v, 6)) in voxset for v in nz[:200])
+    td, tl, tf = oracle.backproject(case["data"], case["label"], case["depth"], case["meta"], case["label_3d"], 16, 3, 0.02)
+    assert td.shape == (1, 16, 16, 16, 4) and tl.shape == (1, 16, 16, 16, 3) and tf.shape == td.shape
+    assert set(np.unique(tf)) <= {0.0, 1.0}
+    empty = tf[..., 0] == 0
+    np.testing.assert_array_equal(tl[empty], case["label_3d"][empty])      # fallback to label_3d
+    assert (td[empty] == 0).all()
+
+
+def test_oracle_average_distance_properties():
+    pts = synth.make_model_points(22, 200)
+    sym = synth.LOV_SYMMETRY
+    pred, targ, wt = synth.make_pose_batch(8, 22, seed=3)
+    loss, diff = oracle.average_distance_loss(pred, targ, wt, pts, sym, 0.01)
+    assert loss.shape == (1,) and diff.shape == pred.shape and loss[0] >= 0
+    assert (diff[wt == 0] == 0).all()
+    # identical prediction and target -> zero distance -> below the margin -> zero loss and gradient
+    loss0, diff0 = oracle.average_distance_loss(targ, targ, wt, pts, sym, 0.01)
+    assert loss0[0] == 0 and not diff0.any()
+    # finite-difference check of d loss / d q on a non-symmetric class with margin 0
+    n = [i for i in range(8) if wt[i].any() and sym[int(np.argmax(wt[i]) // 4)] == 0][0]
+    c = int(np.argmax(wt[n]) // 4)
+    l0, d0 = oracle.average_distance_loss(pred, targ, wt, pts, sym, 0.0)
+    for k in range(4):
+        p2 = pred.copy(); p2[n, 4 * c + k] += 1e-3
+        l1, _ = oracle.average_distance_loss(p2, targ, wt, pts, sym, 0.0)
+        fd = (l1[0] - l0[0]) / 1e-3
+        assert abs(fd - d0[n, 4 * c + k]) < 5e-3 * max(1.0, abs(fd)), (k, fd, d0[n, 4 * c + k])
