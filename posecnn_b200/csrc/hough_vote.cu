@@ -15,18 +15,23 @@
 //   evaluation wherever that predicate is monotone along the row (everywhere outside
 //   rounding distance of the threshold).
 //
-//   k_hist     per-chunk class histogram (+ zero-fill of the output buffers)
-//   k_scan     per-image exclusive scan of chunk histograms, class filter (>label_threshold)
-//   k_emit     deterministic raster-order ranks; every skip-th pixel of a class becomes a
-//              32-byte sample record (direction, depth, window, boundary-ray slopes)
-//   k_worklist (image, class, 32-row band) work items inside each class's vote bounding box
+//   k_hist     per-chunk class histogram and class totals (+ zero-fill of the output buffers)
+//   k_emit     class filter (> label_threshold), deterministic raster-order ranks; every skip-th
+//              pixel of a class becomes a 32-byte sample record (direction, depth, window,
+//              boundary-ray slopes); records are built on densely packed lanes from a smem queue
+//   k_worklist (image, class, 16-row band) work items inside each class's vote bounding box,
+//              heaviest classes first
 //   k_vote     persistent CTAs: difference array of a band in shared memory, shared-memory
-//              atomics (2 per sample-row), row prefix scan fused with the arg-max
+//              atomics (2 per sample-row), row prefix scan fused with the arg-max; end points
+//              that fall within rounding distance of a cell are queued per warp and re-checked
+//              with the reference predicate on densely packed lanes
 //   k_select / k_localmax   maxima (first arg-max per class, or 7x7 local maxima)
 //   k_celldata per selected cell: exact recount, mean depth, box extents (second pass of the
 //              reference kernel, done only for selected cells)
 //   k_finalize ROI cap, row offsets, ROI / pose / target / weight / domain rows
 #include <float.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -57,9 +62,10 @@ struct Layout {
 
 static int band_rows(int W)
 {
-    // difference array of one band: R rows x (W + 3) ints, kept under ~100 KB so two CTAs fit per SM
-    int R = 32;
-    while (R > 1 && (size_t)R * (W + 3) * 4 > 100 * 1024) R >>= 1;
+    // difference array of one band: R rows x (W + 3) ints; 16 rows = 41 KB at W = 640, so four
+    // CTAs (32 warps) fit per SM and the work items are fine grained enough to balance
+    int R = 16;
+    while (R > 1 && (size_t)R * (W + 3) * 4 > 48 * 1024) R >>= 1;
     return R;
 }
 
@@ -153,7 +159,8 @@ struct ZeroList {
 };
 
 __global__ void __launch_bounds__(kThreads)
-k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restrict__ chunk_hist, ZeroList z)
+k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restrict__ chunk_hist, int* __restrict__ cls_size,
+       int* __restrict__ bbox, int* __restrict__ cand_n, int* __restrict__ work_ctr, ZeroList z)
 {
     extern __shared__ int sh[];
     const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x, lane = t & 31;
@@ -164,6 +171,16 @@ k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restric
 #pragma unroll
         for (int k = 0; k < 5; k++)
             for (unsigned i = gid; i < z.n[k]; i += gsz) z.p[k][i] = 0.f;
+    }
+    if (chunk == 0) {  // per-image state consumed by the later kernels
+        for (int c = t; c < C; c += kThreads) {
+            int* bb = bbox + ((size_t)b * C + c) * 4;
+            bb[0] = 0x7fffffff; bb[1] = -1; bb[2] = 0x7fffffff; bb[3] = -1;
+        }
+        if (t == 0) {
+            cand_n[b] = 0;
+            if (b == 0) { work_ctr[0] = 0; work_ctr[1] = 0; }
+        }
     }
     for (int c = t; c < C; c += kThreads) sh[c] = 0;
     __syncthreads();
@@ -178,54 +195,10 @@ k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restric
     }
     __syncthreads();
     int* out = chunk_hist + ((size_t)b * nchunks + chunk) * C;
-    for (int c = t; c < C; c += kThreads) out[c] = sh[c];
-}
-
-// ----------------------------------------------------------------------------------------
-// k_scan: exclusive scan over chunks per (image, class); class filter and sample offsets
-// (class_indexes of .cu.cc:650-663, built on the device)
-// ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_scan(int C, int nchunks, int skip, int label_thr, int* __restrict__ chunk_hist, int* __restrict__ cls_size,
-       int* __restrict__ cls_slot, int* __restrict__ cls_nsamp, int* __restrict__ cls_soff,
-       int* __restrict__ slot_cls, int* __restrict__ img_count, int* __restrict__ bbox, int* __restrict__ cand_n,
-       int* __restrict__ work_ctr)
-{
-    const int b = blockIdx.x, t = threadIdx.x;
     for (int c = t; c < C; c += kThreads) {
-        int* h = chunk_hist + (size_t)b * nchunks * C + c;
-        int run = 0;
-        for (int k = 0; k < nchunks; k++) {
-            int v = h[(size_t)k * C];
-            h[(size_t)k * C] = run;
-            run += v;
-        }
-        cls_size[b * C + c] = run;
-    }
-    __syncthreads();
-    if (t == 0) {
-        int slot = 0, soff = 0;
-        for (int c = 0; c < C; c++) {
-            int sz = cls_size[b * C + c];
-            if (c > 0 && sz > label_thr) {
-                int ns = (sz + skip - 1) / skip;
-                cls_slot[b * C + c] = slot;
-                slot_cls[b * C + slot] = c;
-                cls_nsamp[b * C + c] = ns;
-                cls_soff[b * C + c] = soff;
-                soff += ns;
-                slot++;
-            } else {
-                cls_slot[b * C + c] = -1;
-                cls_nsamp[b * C + c] = 0;
-                cls_soff[b * C + c] = 0;
-            }
-            int* bb = bbox + ((size_t)b * C + c) * 4;
-            bb[0] = 0x7fffffff; bb[1] = -1; bb[2] = 0x7fffffff; bb[3] = -1;
-        }
-        img_count[b] = slot;
-        cand_n[b] = 0;
-        if (b == 0) { work_ctr[0] = 0; work_ctr[1] = 0; }
+        int v = sh[c];
+        out[c] = v;
+        if (v) atomicAdd(&cls_size[b * C + c], v);  // class totals (zeroed by the host-side memset node)
     }
 }
 
@@ -236,13 +209,66 @@ k_scan(int C, int nchunks, int skip, int label_thr, int* __restrict__ chunk_hist
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const float* __restrict__ extents,
-       const float* __restrict__ meta_all, int H, int W, int C, int num_meta, int nchunks, int skip, float inlier,
-       const int* __restrict__ chunk_prefix, const int* __restrict__ cls_slot, const int* __restrict__ cls_soff,
+       const float* __restrict__ meta_all, int H, int W, int C, int num_meta, int nchunks, int skip, int label_thr,
+       float inlier, const int* __restrict__ chunk_hist, const int* __restrict__ cls_size, int* __restrict__ cls_slot,
+       int* __restrict__ cls_nsamp, int* __restrict__ cls_soff, int* __restrict__ slot_cls, int* __restrict__ img_count,
        Sample* __restrict__ samples, int samp_cap, int* __restrict__ bbox)
 {
-    extern __shared__ int wh[];  // [kWarps][C]
+    // smem: [kWarps][C] warp histograms | [C][4] block bounding boxes | [C] slot | [C] sample offset | [C] chunk prefix
+    //       | [kChunk] int2 sample queue
+    extern __shared__ int wh[];
     const int b = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int HW = H * W;
+    int* sbb = wh + kWarps * C;
+    int* s_slot = sbb + 4 * C;
+    int* s_soff = s_slot + C;
+    int* s_pref = s_soff + C;
+    // class table of this image (class_indexes of .cu.cc:650-663): classes with more than label_thr pixels,
+    // ascending; sample offsets = running sum of ceil(size / skip).  Every CTA recomputes it (C is small),
+    // the CTA of chunk 0 publishes it for the later kernels.
+    if (w == 0) {
+        int slot_run = 0, soff_run = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane;
+            const int sz = c < C ? cls_size[b * C + c] : 0;
+            const bool present = c > 0 && c < C && sz > label_thr;
+            const int ns = present ? (sz + skip - 1) / skip : 0;
+            const unsigned pm = __ballot_sync(0xffffffffu, present);
+            int incl = ns;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            const int slot = slot_run + __popc(pm & ((1u << lane) - 1u));
+            const int soff = soff_run + incl - ns;
+            if (c < C) {
+                s_slot[c] = present ? slot : -1;
+                s_soff[c] = soff;
+                if (chunk == 0) {
+                    cls_slot[b * C + c] = present ? slot : -1;
+                    cls_nsamp[b * C + c] = ns;
+                    cls_soff[b * C + c] = present ? soff : 0;
+                    if (present) slot_cls[b * C + slot] = c;
+                }
+            }
+            slot_run += __popc(pm);
+            soff_run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (chunk == 0 && lane == 0) img_count[b] = slot_run;
+    }
+    for (int i = t; i < kWarps * C; i += kThreads) wh[i] = 0;
+    for (int i = t; i < C; i += kThreads) { sbb[4 * i] = 0x7fffffff; sbb[4 * i + 1] = -1; sbb[4 * i + 2] = 0x7fffffff; sbb[4 * i + 3] = -1; }
+    __syncthreads();
+    // pixels of this class in earlier chunks of the image (one warp per class, lanes over chunks)
+    for (int c = w; c < C; c += kWarps) {
+        int sum = 0;
+        if (s_slot[c] >= 0)
+            for (int k = lane; k < chunk; k += 32) sum += chunk_hist[((size_t)b * nchunks + k) * C + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) s_pref[c] = sum;
+    }
     const int* lab = label + (size_t)b * HW;
     const int base = chunk * kChunk + w * (kChunk / kWarps);
     int labs[kChunk / kThreads];
@@ -250,11 +276,9 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
     for (int s = 0; s < kChunk / kThreads; s++) {
         int p = base + s * 32 + lane;
         int cls = p < HW ? lab[p] : -1;
-        if (!(cls > 0 && cls < C) || cls_slot[b * C + cls] < 0) cls = -1;
+        if (!(cls > 0 && cls < C) || s_slot[cls] < 0) cls = -1;
         labs[s] = cls;
     }
-    for (int i = t; i < kWarps * C; i += kThreads) wh[i] = 0;
-    __syncthreads();
 #pragma unroll
     for (int s = 0; s < kChunk / kThreads; s++) {
         int cls = labs[s];
@@ -264,7 +288,7 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
     }
     __syncthreads();
     for (int c = t; c < C; c += kThreads) {
-        int run = chunk_prefix[((size_t)b * nchunks + chunk) * C + c];
+        int run = s_pref[c];
 #pragma unroll
         for (int ww = 0; ww < kWarps; ww++) {
             int tmp = wh[ww * C + c];
@@ -275,6 +299,12 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
     __syncthreads();
     const float* meta = meta_all + (size_t)b * num_meta;
     const unsigned lt = (1u << lane) - 1u;
+    // pass 2: ranks; sampled pixels are queued in shared memory so that the (divergent, ~600
+    // instruction) record construction below runs on densely packed lanes
+    int2* queue = reinterpret_cast<int2*>(wh + (((kWarps + 7) * C + 1) & ~1));  // [kChunk] (pixel offset in chunk | class << 16, sample index)
+    __shared__ int s_qn;
+    if (t == 0) s_qn = 0;
+    __syncthreads();
 #pragma unroll
     for (int s = 0; s < kChunk / kThreads; s++) {
         int cls = labs[s];
@@ -285,7 +315,17 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
         if (cls >= 0 && lane == __ffs(peers) - 1) wh[w * C + cls] += __popc(peers);
         __syncwarp();
         if (cls >= 0 && rank % skip == 0) {
-            int p = base + s * 32 + lane;
+            int pos = atomicAdd(&s_qn, 1);
+            queue[pos] = make_int2((w * (kChunk / kWarps) + s * 32 + lane) | (cls << 16), rank / skip);
+        }
+    }
+    __syncthreads();
+    const int qn = s_qn;
+    for (int qi = t; qi < qn; qi += kThreads) {
+        const int2 qe = queue[qi];
+        const int cls = qe.x >> 16;
+        const int p = chunk * kChunk + (qe.x & 0xffff);
+        {
             int x = p % W, y = p / W;
             size_t off = (size_t)3 * cls + (size_t)3 * C * ((size_t)b * HW + p);
             float u = vertex[off], v = vertex[off + 1], z = vertex[off + 2];
@@ -304,54 +344,82 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
             float r2x = ca * uh + sa * vh, r2y = ca * vh - sa * uh;
             float k1 = r1x / r1y, k2 = r2x / r2y;
             int flags = (r1y > 0.f ? 1 : 0) | (r1y < 0.f ? 2 : 0) | (r2y > 0.f ? 4 : 0) | (r2y < 0.f ? 8 : 0) |
-                        ((r2x - r2y * k1) > 0.f ? 16 : 0) | ((r1x - r1y * k2) > 0.f ? 32 : 0);
+                        ((r2x - r2y * k1) > 0.f ? 16 : 0) | ((r1x - r1y * k2) > 0.f ? 32 : 0) |
+                        (pred_exact(u, v, n1, 1.f, 0.f, inlier) ? 64 : 0) | (pred_exact(u, v, n1, -1.f, 0.f, inlier) ? 128 : 0);
             Sample rec;
             rec.xy = x | (y << 16);
             rec.u = u; rec.v = v; rec.n1 = n1; rec.k1 = k1; rec.k2 = k2;
             rec.mflags = (m & 0xffff) | (flags << 16);
             rec.d = d;
-            Sample* dst = samples + (size_t)b * samp_cap + cls_soff[b * C + cls] + rank / skip;
+            Sample* dst = samples + (size_t)b * samp_cap + s_soff[cls] + qe.y;
             reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(&rec)[0];
             reinterpret_cast<float4*>(dst)[1] = reinterpret_cast<const float4*>(&rec)[1];
             if (m >= 0) {
-                int* bb = bbox + ((size_t)b * C + cls) * 4;
-                atomicMin(&bb[0], max(y - m, 0));
-                atomicMax(&bb[1], min(y + m, H - 1));
-                atomicMin(&bb[2], max(x - m, 0));
-                atomicMax(&bb[3], min(x + m, W - 1));
+                atomicMin(&sbb[4 * cls + 0], max(y - m, 0));
+                atomicMax(&sbb[4 * cls + 1], min(y + m, H - 1));
+                atomicMin(&sbb[4 * cls + 2], max(x - m, 0));
+                atomicMax(&sbb[4 * cls + 3], min(x + m, W - 1));
             }
         }
     }
+    __syncthreads();
+    for (int c = t; c < C; c += kThreads)
+        if (sbb[4 * c + 1] >= 0) {
+            int* bb = bbox + ((size_t)b * C + c) * 4;
+            atomicMin(&bb[0], sbb[4 * c]);
+            atomicMax(&bb[1], sbb[4 * c + 1]);
+            atomicMin(&bb[2], sbb[4 * c + 2]);
+            atomicMax(&bb[3], sbb[4 * c + 3]);
+        }
 }
 
 // ----------------------------------------------------------------------------------------
 // k_worklist: (image, slot, band) items for every band that intersects a class's vote box
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(1024)
 k_worklist(int B, int C, int R, int nbands, const int* __restrict__ img_count, const int* __restrict__ slot_cls,
-           const int* __restrict__ bbox, int* __restrict__ work, int* __restrict__ work_ctr)
+           const int* __restrict__ cls_nsamp, const int* __restrict__ bbox, int* __restrict__ work,
+           int* __restrict__ work_ctr)
 {
-    __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = 0;
+    // Items are laid out by (coarsely) descending sample count of their class: longest first keeps the
+    // persistent k_vote CTAs balanced.  The order has no effect on results.  Counting sort on 64 buckets.
+    __shared__ int s_cnt[64];
+    __shared__ int s_base[64];
+    const int n = B * C;
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < B * C; i += kThreads) {
+    auto bucket = [](int ns) { return 63 - min(63, ns >> 8); };  // 256 samples per bucket, big classes first
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int b = i / C, slot = i % C;
         if (slot >= img_count[b]) continue;
         int c = slot_cls[b * C + slot];
         const int* bb = bbox + ((size_t)b * C + c) * 4;
         if (bb[1] < bb[0]) continue;
-        int lo = bb[0] / R, hi = bb[1] / R;
-        int pos = atomicAdd(&s_n, hi - lo + 1);
-        for (int k = lo; k <= hi; k++) work[pos++] = (b * C + slot) * nbands + k;
+        atomicAdd(&s_cnt[bucket(cls_nsamp[b * C + c])], bb[1] / R - bb[0] / R + 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { work_ctr[0] = 0; work_ctr[1] = s_n; }
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; k++) { s_base[k] = run; run += s_cnt[k]; }
+        work_ctr[0] = 0; work_ctr[1] = run;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int b = i / C, slot = i % C;
+        if (slot >= img_count[b]) continue;
+        int c = slot_cls[b * C + slot];
+        const int* bb = bbox + ((size_t)b * C + c) * 4;
+        if (bb[1] < bb[0]) continue;
+        int lo = bb[0] / R, nb = bb[1] / R - lo + 1;
+        int pos = atomicAdd(&s_base[bucket(cls_nsamp[b * C + c])], nb);
+        for (int k = 0; k < nb; k++) work[pos + k] = (b * C + slot) * nbands + lo + k;
+    }
 }
 
 // ----------------------------------------------------------------------------------------
 // k_vote: persistent CTAs; one (image, class, band) difference array in shared memory
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restrict__ slot_cls,
        const int* __restrict__ cls_nsamp, const int* __restrict__ cls_soff, const int* __restrict__ bbox,
        const Sample* __restrict__ samples, int samp_cap, const int* __restrict__ work, int* __restrict__ work_ctr,
@@ -361,8 +429,13 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
     __shared__ int s_item;
     __shared__ int s_red_val[kWarps];
     __shared__ int s_red_idx[kWarps];
+    __shared__ int4 s_q[kWarps][64];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int total = work_ctr[1];
+    // a warp covers 32 / R samples x R rows per iteration (R is a power of two <= 32)
+    const int rl = lane & (R - 1);   // row of the band owned by this lane
+    const int sub = lane / R;        // which of the warp's samples
+    const int spw = 32 / R;
     while (true) {
         __syncthreads();
         if (t == 0) s_item = atomicAdd(&work_ctr[0], 1);
@@ -383,63 +456,138 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
 
         const int ns = cls_nsamp[b * C + c];
         const Sample* S = samples + (size_t)b * samp_cap + cls_soff[b * C + c];
-        const int cy = r0 + lane;
-        int* Drow = D + lane * stride - xlo;
-        for (int s = w; s < ns; s += kWarps) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(S + s));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(S + s) + 1);
+        const int cy = r0 + rl;
+        int* Drow = D + rl * stride - xlo;
+        int4* Q = s_q[w];   // this warp's queue of (sample, row) pairs whose end points need the exact check
+        int qn = 0;         // warp-uniform
+        const unsigned lt = (1u << lane) - 1u;
+
+        // Re-check of queued pairs with the reference predicate, on densely packed lanes.
+        auto drain = [&](int count) {
+            if (lane < count) {
+                const int4 q = Q[lane];
+                const Sample* rp = S + q.x;
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(rp));
+                const int mfl = __float_as_int(__ldg(reinterpret_cast<const float*>(rp) + 6));
+                const int xy = __float_as_int(q0.x);
+                const int x = xy & 0xffff, y = xy >> 16, m = (int)(short)(mfl & 0xffff);
+                const int row = q.y & 0xff, mode = q.y >> 8;
+                const float u = q0.y, v = q0.z, n1 = q0.w;
+                const float dy = (float)(r0 + row - y);
+                const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
+                const float tn1 = inlier * n1, vdy = __fmul_rn(v, dy), dy2 = dy * dy;
+                auto P = [&](int cx) { return pred_fast(u, v, n1, tn1, (float)(cx - x), dy, vdy, dy2, inlier); };
+                int a = q.z, e = q.w;
+                bool ok = true;
+                if (mode & 12) {
+                    ok = false;
+                    if ((mode & 4) && P(a)) { e = a; ok = true; }
+                    else if ((mode & 8) && P(e)) { a = e; ok = true; }
+                } else {
+#pragma unroll 1
+                    for (int side = 0; side < 2 && ok; side++) {
+                        if (!(mode & (1 << side))) continue;
+                        const int o = side ? 1 : -1, lim = side ? wmax : wmin;
+                        int pc = side ? e : a;
+                        while (pc != lim && P(pc + o)) pc += o;                        // grow outwards while cells pass
+                        while ((side ? pc >= a : pc <= e) && !P(pc)) pc -= o;          // shrink inwards while they fail
+                        if (side) e = pc; else a = pc;
+                        ok = a <= e;
+                    }
+                }
+                if (ok) {
+                    int* Dq = D + row * stride - xlo;
+                    atomicAdd(&Dq[a], 1);
+                    atomicAdd(&Dq[e + 1], -1);
+                }
+            }
+            __syncwarp();
+        };
+
+        // software pipeline: the record of the next iteration is in flight while this one is processed
+        int sidx = w * spw + sub;
+        float4 n0 = make_float4(0, 0, 0, 0), n1v = n0;
+        if (sidx < ns) {
+            n0 = __ldg(reinterpret_cast<const float4*>(S + sidx));
+            n1v = __ldg(reinterpret_cast<const float4*>(S + sidx) + 1);
+        }
+        for (int sb = w * spw; sb < ns; sb += kWarps * spw) {
+            const float4 q0 = n0, q1 = n1v;
+            const int scur = sidx;
+            sidx += kWarps * spw;
+            if (sidx < ns) {
+                n0 = __ldg(reinterpret_cast<const float4*>(S + sidx));
+                n1v = __ldg(reinterpret_cast<const float4*>(S + sidx) + 1);
+            }
             const int xy = __float_as_int(q0.x);
             const int x = xy & 0xffff, y = xy >> 16;
             const int mflags = __float_as_int(q1.z);
             const int m = (int)(short)(mflags & 0xffff);
+            const int fl = mflags >> 16;
             const int idy = cy - y;
-            if (lane >= nrows || m < 0 || abs(idy) > m) continue;
-            const float u = q0.y, v = q0.z, n1 = q0.w;
-            const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
-            const float tn1 = inlier * n1;
-            const float dy = (float)idy;
-            int a, e;  // candidate interval [a, e]
-            if (idy == 0) {
-                // on the pixel's own row cos = sign(dx) * u / n1 (the pixel itself gives 0/0 = NaN: no vote)
-                if (pred_exact(u, v, n1, 1.f, 0.f, inlier)) { a = x + 1; e = wmax; }
-                else if (pred_exact(u, v, n1, -1.f, 0.f, inlier)) { a = wmin; e = x - 1; }
-                else continue;
-                if (a > e) continue;
-            } else {
-                const int fl = mflags >> 16;
-                const bool v1 = idy > 0 ? (fl & 1) : (fl & 2);
-                const bool v2 = idy > 0 ? (fl & 4) : (fl & 8);
-                if (!v1 && !v2) continue;
-                const float h1 = dy * q1.x, h2 = dy * q1.y;
-                float lo, hi;
-                if (v1 && v2) { lo = fminf(h1, h2); hi = fmaxf(h1, h2); }
-                else if (v1) { if (fl & 16) { lo = h1; hi = 1e9f; } else { lo = -1e9f; hi = h1; } }
-                else { if (fl & 32) { lo = h2; hi = 1e9f; } else { lo = -1e9f; hi = h2; } }
-                lo = fminf(fmaxf(lo, -40000.f), 40000.f);
-                hi = fminf(fmaxf(hi, -40000.f), 40000.f);
-                a = max(wmin, x + (int)ceilf(lo));
-                e = min(wmax, x + (int)floorf(hi));
-                // snap both ends with the reference predicate
-                const float vdy = __fmul_rn(v, dy), dy2 = dy * dy;
-                auto P = [&](int cx) { return pred_fast(u, v, n1, tn1, (float)(cx - x), dy, vdy, dy2, inlier); };
-                if (a > e) {
-                    // estimated empty: the only cells that can still pass sit at the estimate itself
-                    int c0 = min(max(a, wmin), wmax);
-                    if (P(c0)) { a = e = c0; }
-                    else {
-                        int c1 = min(max(e, wmin), wmax);
-                        if (c1 != c0 && P(c1)) { a = e = c1; } else continue;
+            int act = 0;      // 0 nothing, 1 interval [a, e] trusted, 2 queued for the exact check
+            int a = 0, e = 0, mode = 0;
+            if (scur < ns && rl < nrows && m >= 0 && abs(idy) <= m) {
+                const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
+                if (idy == 0) {
+                    // the pixel's own row: cos = sign(dx) * u / n1, decided once per sample in k_emit
+                    if (fl & 64) { a = x + 1; e = wmax; act = a <= e; }
+                    else if (fl & 128) { a = wmin; e = x - 1; act = a <= e; }
+                } else {
+                    const bool v1 = idy > 0 ? (fl & 1) : (fl & 2);
+                    const bool v2 = idy > 0 ? (fl & 4) : (fl & 8);
+                    if (v1 || v2) {
+                        const float dy = (float)idy;
+                        const float h1 = dy * q1.x, h2 = dy * q1.y;
+                        float lo, hi;
+                        if (v1 && v2) { lo = fminf(h1, h2); hi = fmaxf(h1, h2); }
+                        else {
+                            const float hh = v1 ? h1 : h2;
+                            const bool up = v1 ? (fl & 16) : (fl & 32);
+                            lo = up ? hh : -1e9f;
+                            hi = up ? 1e9f : hh;
+                        }
+                        lo = fminf(fmaxf(lo, -40000.f), 40000.f);
+                        hi = fminf(fmaxf(hi, -40000.f), 40000.f);
+                        a = x + (int)ceilf(lo);
+                        e = x + (int)floorf(hi);
+                        // The ray estimate and the fp32 predicate both sit within ~1e-6 (dy^2 + m^2) / |dy| cells
+                        // of the real cone boundary; an end point closer than tau to an integer
+                        // is re-checked with the reference predicate, the others are exact as they are.
+                        const float tau = 0.03f + 2e-6f * __fdividef(dy * dy + (float)(m * m), fabsf(dy));
+                        if (a > e) {
+                            const bool ca = (float)(a - x) - hi < tau && a >= wmin && a <= wmax;
+                            const bool ce = lo - (float)(e - x) < tau && e >= wmin && e <= wmax;
+                            if (ca || ce) { act = 2; mode = (ca ? 4 : 0) | (ce ? 8 : 0); }
+                        } else {
+                            const float ma = (float)(a - x) - lo, me = hi - (float)(e - x);
+                            const bool va = a >= wmin && (ma < tau || ma > 1.f - tau);
+                            const bool ve = e <= wmax && (me < tau || me > 1.f - tau);
+                            a = max(a, wmin);
+                            e = min(e, wmax);
+                            if (a <= e) { act = (va || ve) ? 2 : 1; mode = (va ? 1 : 0) | (ve ? 2 : 0); }
+                        }
                     }
                 }
-                while (a > wmin && P(a - 1)) a--;
-                while (a <= e && !P(a)) a++;
-                if (a > e) continue;
-                while (e < wmax && P(e + 1)) e++;
-                while (e > a && !P(e)) e--;
             }
-            atomicAdd(&Drow[a], 1);
-            atomicAdd(&Drow[e + 1], -1);
+            if (act == 1) {
+                atomicAdd(&Drow[a], 1);
+                atomicAdd(&Drow[e + 1], -1);
+            }
+            const unsigned need = __ballot_sync(0xffffffffu, act == 2);
+            if (need) {
+                if (act == 2) Q[qn + __popc(need & lt)] = make_int4(scur, rl | (mode << 8), a, e);
+                qn += __popc(need);
+                __syncwarp();
+                if (qn >= 32) {
+                    drain(32);
+                    if (lane < qn - 32) Q[lane] = Q[32 + lane];
+                    qn -= 32;
+                    __syncwarp();
+                }
+            }
         }
+        if (qn > 0) drain(qn);
         __syncthreads();
 
         // row prefix sums fused with the arg-max (first maximum in flat index order)
@@ -569,7 +717,8 @@ k_celldata(int B, int H, int W, int C, int num_meta, float inlier, int cand_cap,
     __shared__ float s_thr2;
     const int t = threadIdx.x;
     const int HW = H * W;
-    for (int b = 0; b < B; b++) {
+    {
+        const int b = blockIdx.y;  // grid = (candidate lanes per image, B)
         const int n = min(cand_n[b], cand_cap);
         for (int i = blockIdx.x; i < n; i += gridDim.x) {
             const int key = cand_key[(size_t)b * cand_cap + i];
@@ -823,20 +972,20 @@ static int run_front(const Layout& L, char* ws, const int32_t* label, const floa
     int* cand_n = (int*)(ws + L.cand_n);
     const int HW = H * W;
     dim3 grid(L.nchunks, B);
-    k_hist<<<grid, kThreads, sizeof(int) * C, st>>>(label, HW, C, L.nchunks, chunk_hist, z);
-    k_scan<<<B, kThreads, 0, st>>>(C, L.nchunks, skip, label_thr, chunk_hist, cls_size, cls_slot, cls_nsamp, cls_soff,
-                                   slot_cls, img_count, bbox, cand_n, work_ctr);
-    k_emit<<<grid, kThreads, sizeof(int) * kWarps * C, st>>>(label, vertex, extents, meta, H, W, C, num_meta, L.nchunks,
-                                                             skip, inlier, chunk_hist, cls_slot, cls_soff, samples,
-                                                             L.samp_cap, bbox);
-    k_worklist<<<1, kThreads, 0, st>>>(B, C, L.R, L.nbands, img_count, slot_cls, bbox, work, work_ctr);
+    cudaMemsetAsync(cls_size, 0, sizeof(int) * (size_t)B * C, st);
+    k_hist<<<grid, kThreads, sizeof(int) * C, st>>>(label, HW, C, L.nchunks, chunk_hist, cls_size, bbox, cand_n, work_ctr, z);
+    const size_t emit_smem = sizeof(int) * ((((kWarps + 7) * C + 1) & ~1) + 2 * kChunk);
+    k_emit<<<grid, kThreads, emit_smem, st>>>(label, vertex, extents, meta, H, W, C, num_meta, L.nchunks, skip, label_thr,
+                                              inlier, chunk_hist, cls_size, cls_slot, cls_nsamp, cls_soff, slot_cls,
+                                              img_count, samples, L.samp_cap, bbox);
+    k_worklist<<<1, 1024, 0, st>>>(B, C, L.R, L.nbands, img_count, slot_cls, cls_nsamp, bbox, work, work_ctr);
     size_t smem = sizeof(int) * (size_t)L.R * (W + 3);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         attr_set = true;
     }
-    k_vote<<<2 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, slot_cls, cls_nsamp, cls_soff, bbox,
+    k_vote<<<4 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, slot_cls, cls_nsamp, cls_soff, bbox,
                                                 samples, L.samp_cap, work, work_ctr, band_res, votes_out);
     return check_launch("hough front kernels");
 }
@@ -847,7 +996,7 @@ static int validate(int B, int H, int W, int C, int skip)
     PCNN_REQUIRE(H <= 16383 && W <= 16383, "hough: image larger than 16383 x 16383 unsupported (got %d x %d)", W, H);
     PCNN_REQUIRE((long long)C * H * W < 0x7fffffffLL, "hough: C*H*W must fit int32 (reference flat index, .cu.cc:260)");
     PCNN_REQUIRE(skip >= 1, "hough: skip_pixels must be >= 1 (got %d)", skip);
-    PCNN_REQUIRE(C <= 1024, "hough: at most 1024 classes supported (got %d)", C);
+    PCNN_REQUIRE(C <= 512, "hough: at most 512 classes supported (got %d)", C);
     return PCNN_OK;
 }
 
@@ -924,7 +1073,8 @@ extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, co
         k_localmax<<<g, kThreads, 0, st>>>(H, W, C, L.R, threshold_vote, L.cand_cap, img_count, slot_cls, bbox, votes,
                                            cand_key, cand_val, cand_n, status);
     }
-    k_celldata<<<kNumSMs, kThreads, 0, st>>>(B, H, W, C, num_meta, inlier_threshold, L.cand_cap, extents, meta, slot_cls,
+    dim3 gcell(thr_mode ? 64 : (unsigned)std::max(1, std::min(std::min(cap, C), L.cand_cap)), B);
+    k_celldata<<<gcell, kThreads, 0, st>>>(B, H, W, C, num_meta, inlier_threshold, L.cand_cap, extents, meta, slot_cls,
                                              (const int*)(ws + L.cls_nsamp), (const int*)(ws + L.cls_soff),
                                              (const Sample*)(ws + L.samples), L.samp_cap, cand_key, cand_n, cand_data);
     k_finalize<<<1, kThreads, 0, st>>>(B, H, W, C, num_meta, num_gt, is_train, cap, L.cand_cap, thr_mode ? 1 : 0,

@@ -128,34 +128,72 @@ k_roi_pool_fwd_cls(const float* __restrict__ bottom, const float* __restrict__ r
 }
 
 // RoiPool backward as a scatter through argmax: grad_in[b, argmax] += top_diff.  The
-// reference gathers per input element over ALL rois (.cu.cc:153); the set of (bin, element)
-// pairs that contribute is identical: a bin contributes to an element iff its argmax is that
-// element (the feasibility tests of .cu.cc:169-204 are implied by how argmax was produced).
+// reference gathers per input element over ALL rois (.cu.cc:153) and accepts a (bin, element)
+// pair iff the element lies inside the un-clipped roi (.cu.cc:176-181), the bin lies in the
+// element's feasible bin range (.cu.cc:203-211) and the bin's argmax is that element; the
+// same three tests are applied here per pooled value, so the set of contributions is identical
+// (malformed rois, whose forward is forced to 1x1, contribute nothing — as in the reference).
+struct RoiGeom {
+    int b, rsw, rsh, rew, reh;
+    float bh, bw;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ r, float scale, int ph_n, int pw_n)
+{
+    RoiGeom g;
+    g.b = (int)r[0];
+    g.rsw = (int)roundf(__fmul_rn(r[2], scale)); g.rsh = (int)roundf(__fmul_rn(r[3], scale));
+    g.rew = (int)roundf(__fmul_rn(r[4], scale)); g.reh = (int)roundf(__fmul_rn(r[5], scale));
+    int rw = max(g.rew - g.rsw + 1, 1), rh = max(g.reh - g.rsh + 1, 1);
+    g.bh = __fdiv_rn((float)rh, (float)ph_n);
+    g.bw = __fdiv_rn((float)rw, (float)pw_n);
+    return g;
+}
+
+__device__ __forceinline__ bool roi_bwd_accepts(const RoiGeom& g, int a, int width, int channels, int ph, int pw, int ph_n,
+                                                int pw_n)
+{
+    int pix = a / channels;
+    int h = pix / width, w = pix % width;
+    if (!(w >= g.rsw && w <= g.rew && h >= g.rsh && h <= g.reh)) return false;
+    int phs = (int)floorf(__fdiv_rn((float)(h - g.rsh), g.bh)), phe = (int)ceilf(__fdiv_rn((float)(h - g.rsh + 1), g.bh));
+    int pws = (int)floorf(__fdiv_rn((float)(w - g.rsw), g.bw)), pwe = (int)ceilf(__fdiv_rn((float)(w - g.rsw + 1), g.bw));
+    phs = min(max(phs, 0), ph_n); phe = min(max(phe, 0), ph_n);
+    pws = min(max(pws, 0), pw_n); pwe = min(max(pwe, 0), pw_n);
+    return ph >= phs && ph < phe && pw >= pws && pw < pwe;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_roi_pool_bwd(const float* __restrict__ top_diff, const int* __restrict__ argmax, const float* __restrict__ rois,
-               int batch, int num_rois, int channel_rois, int height, int width, int channels, int out_ch, int bins,
-               float* __restrict__ bottom_diff)
+               int batch, int num_rois, int channel_rois, int height, int width, int channels, int out_ch, int ph_n,
+               int pw_n, float scale, float* __restrict__ bottom_diff)
 {
     const int cg = out_ch / VEC;
+    const int bins = ph_n * pw_n;
     const size_t total = (size_t)num_rois * bins * cg;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t e = idx * VEC;
         int n = (int)(e / ((size_t)bins * out_ch));
-        int b = (int)rois[(size_t)n * channel_rois];
-        if (b < 0 || b >= batch) continue;
-        float* img = bottom_diff + (size_t)b * height * width * channels;
+        int bin = (int)((e / out_ch) % bins);
+        int ph = bin / pw_n, pw = bin % pw_n;
+        RoiGeom g = roi_geom(rois + (size_t)n * channel_rois, scale, ph_n, pw_n);
+        if (g.b < 0 || g.b >= batch) continue;
+        float* img = bottom_diff + (size_t)g.b * height * width * channels;
+        int a[VEC];
+        float d[VEC];
         if (VEC == 4) {
-            int4 a = *reinterpret_cast<const int4*>(argmax + e);
-            float4 g = *reinterpret_cast<const float4*>(top_diff + e);
-            if (a.x >= 0) atomicAdd(img + a.x, g.x);
-            if (a.y >= 0) atomicAdd(img + a.y, g.y);
-            if (a.z >= 0) atomicAdd(img + a.z, g.z);
-            if (a.w >= 0) atomicAdd(img + a.w, g.w);
+            int4 av = *reinterpret_cast<const int4*>(argmax + e);
+            float4 dv = *reinterpret_cast<const float4*>(top_diff + e);
+            a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+            d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
         } else {
-            int a = argmax[e];
-            if (a >= 0) atomicAdd(img + a, top_diff[e]);
+            a[0] = argmax[e];
+            d[0] = top_diff[e];
         }
+#pragma unroll
+        for (int k = 0; k < VEC; k++)
+            if (a[k] >= 0 && roi_bwd_accepts(g, a[k], width, channels, ph, pw, ph_n, pw_n)) atomicAdd(img + a[k], d[k]);
     }
 }
 
@@ -384,7 +422,6 @@ extern "C" int pcnn_roi_pool_bwd(const float* top_diff, const int32_t* argmax, c
                                  int pooled_height, int pooled_width, float spatial_scale, int pool_channel,
                                  float* bottom_diff, void* stream)
 {
-    (void)spatial_scale;
     PCNN_REQUIRE(channel_rois >= 6, "rois must have at least 6 columns (got %d)", channel_rois);
     PCNN_REQUIRE(top_diff && argmax && rois && bottom_diff, "roi_pool_grad: NULL tensor pointer");
     PCNN_REQUIRE(batch >= 1 && height >= 1 && width >= 1 && channels >= 1 && num_rois >= 0, "roi_pool_grad: bad shape");
@@ -397,11 +434,13 @@ extern "C" int pcnn_roi_pool_bwd(const float* top_diff, const int32_t* argmax, c
         if (out_ch % 4 == 0 && aligned16(top_diff) && aligned16(argmax)) {
             size_t total = (size_t)num_rois * bins * (out_ch / 4);
             k_roi_pool_bwd<4><<<grid_for(total, 256), 256, 0, st>>>(top_diff, argmax, rois, batch, num_rois, channel_rois,
-                                                                    height, width, channels, out_ch, bins, bottom_diff);
+                                                                    height, width, channels, out_ch, pooled_height,
+                                                                    pooled_width, spatial_scale, bottom_diff);
         } else {
             size_t total = (size_t)num_rois * bins * out_ch;
             k_roi_pool_bwd<1><<<grid_for(total, 256), 256, 0, st>>>(top_diff, argmax, rois, batch, num_rois, channel_rois,
-                                                                    height, width, channels, out_ch, bins, bottom_diff);
+                                                                    height, width, channels, out_ch, pooled_height,
+                                                                    pooled_width, spatial_scale, bottom_diff);
         }
     }
     return check_launch("roi_pool_bwd");
