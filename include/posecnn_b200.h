@@ -139,6 +139,22 @@ int pcnn_average_distance_fwd(const float* prediction, const float* target, cons
 int pcnn_average_distance_bwd(const float* top_diff, const float* bottom_diff, int N, int channels,
                               float* output, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * VGG16 convolution stack on the tensor cores — replaces Network.conv / Network.max_pool
+ * (networks/network.py:159-188, 303-310: tf.nn.conv2d NHWC x HWIO, SAME, stride 1, bias, ReLU;
+ * 2x2/2 max pool) as wired by networks/vgg16_convs.py:80-97, 128-163.
+ * Implicit GEMM on tcgen05 (BF16 operands, FP32 accumulation in TMEM, TMA-fed, im2col folded
+ * into the TMA box coordinates).  Activations are NHWC bf16; weights are [Cout][k*k*Cin] bf16
+ * (tap-major, channel-minor; converted once from the TF HWIO layout).  block_n = 0 picks the
+ * N tile (64 / 128 / 256) from Cout.
+ */
+int pcnn_conv_bf16_tc(const void* in_bf16, const void* weights_bf16, const float* bias, void* out_bf16, int B,
+                      int H, int W, int Cin, int Cout, int ksize, int relu, int block_n, void* stream);
+/* conv1_1 (Cin = 3): in [B,H,W,Cin] f32, weights HWIO [3,3,Cin,Cout] f32 -> out [B,H,W,Cout] bf16 */
+int pcnn_conv3x3_small_cin(const float* in, const float* weights_hwio, const float* bias, void* out_bf16, int B,
+                           int H, int W, int Cin, int Cout, int relu, void* stream);
+int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,47 @@
+"""Host-side bindings of the tensor-core convolution stack (include/posecnn_b200.h,
+posecnn_b200/csrc/conv_tc.cu).  Activations are NHWC torch.bfloat16 CUDA tensors."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+
+def hwio_to_tc(weights_hwio: torch.Tensor) -> torch.Tensor:
+    """TF filter layout [kh, kw, Cin, Cout] f32 (network.py:166-170) -> [Cout][kh*kw*Cin] bf16."""
+    kh, kw, ci, co = weights_hwio.shape
+    return weights_hwio.permute(3, 0, 1, 2).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+
+
+def conv_bf16(x: torch.Tensor, w_tc: torch.Tensor, bias: torch.Tensor, ksize: int, relu: bool, block_n: int = 0,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """x [B,H,W,Cin] bf16, w_tc [Cout, k*k*Cin] bf16, bias [Cout] f32 -> [B,H,W,Cout] bf16."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    assert w_tc.dtype == torch.bfloat16 and w_tc.is_contiguous() and bias.dtype == torch.float32
+    B, H, W, Cin = x.shape
+    Cout = w_tc.shape[0]
+    assert w_tc.shape[1] == ksize * ksize * Cin
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    check(lib().pcnn_conv_bf16_tc(ptr(x), ptr(w_tc), ptr(bias), ptr(out), B, H, W, Cin, Cout, int(ksize), int(bool(relu)),
+                                  int(block_n), stream()))
+    return out
+
+
+def conv3x3_small_cin(x: torch.Tensor, w_hwio: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """conv1_1: x [B,H,W,3] f32, w [3,3,3,Cout] f32 -> [B,H,W,Cout] bf16."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w_hwio.shape[3]
+    out = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    check(lib().pcnn_conv3x3_small_cin(ptr(x), ptr(w_hwio.contiguous()), ptr(bias), ptr(out), B, H, W, Cin, Cout,
+                                       int(bool(relu)), stream()))
+    return out
+
+
+def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
+    B, H, W, C = x.shape
+    out = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
+    check(lib().pcnn_maxpool2x2_bf16(ptr(x), ptr(out), B, H, W, C, stream()))
+    return out

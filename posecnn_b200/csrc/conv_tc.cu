@@ -1,0 +1,557 @@
+// conv_tc.cu — the VGG16 convolution stack on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+// Behavioural spec: Network.conv, lib/networks/network.py:159-188 (NHWC x HWIO, SAME padding,
+// stride 1, bias add, optional ReLU) as wired by lib/networks/vgg16_convs.py:80-97, 128-163.
+// The reference runs tf.nn.conv2d -> cuDNN in fp32; here the convolution is an implicit GEMM
+//
+//      D[m, n] = sum_{tap, c} A_tap[m, c] * Wt[n, tap*Cin + c],      m = pixel of an 8x16 tile
+//
+// with BF16 operands and FP32 accumulation (precision is stated with every number):
+//   * im2col is never materialised: for every filter tap the A operand of a tile is ONE 4-D TMA
+//     box {64 ch, 16 w, 8 h, 1 n} of the NHWC activation tensor at the tap's (dy, dx) offset;
+//     out-of-image coordinates are zero-filled by the TMA unit = SAME padding;
+//   * the box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, which is
+//     exactly the canonical K-major UMMA operand layout, so tcgen05.mma reads it in place;
+//   * accumulators live in TMEM (two stages of BN fp32 columns), the epilogue (bias, ReLU,
+//     bf16 pack) runs out of TMEM while the next tile's MMAs are already being issued;
+//   * warp roles: warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer, warp 5
+//     MMA issuer; persistent CTAs, one per SM, static round-robin tile schedule.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pcnn {
+namespace convtc {
+
+constexpr int kTileH = 8, kTileW = 16, kTileM = kTileH * kTileW;  // 128 output pixels per tile
+constexpr int kKC = 64;                                           // channels per K step (128 B rows)
+constexpr int kABytes = kTileM * kKC * 2;                         // 16 KB
+constexpr int kThreadsConv = 192;
+constexpr int kStageBytes = 16 * 1024;                            // epilogue staging: one 64-channel group
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (forms as in the CUTLASS sm_90 / sm_100 headers; see DESIGN.md §4 for the list)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], BF16 x BF16 -> FP32, one CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 TMEM lanes (one per thread of the warp) x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int bn)
+{
+    // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct ConvParams {
+    int B, H, W, Cin, Cout;
+    int taps, ksize;          // 9 / 3 or 1 / 1
+    int tiles_h, tiles_w, n_tiles_n, total_tiles;
+    int relu;
+    const float* bias;
+};
+
+template <int BN>
+struct SmemPlan {
+    static constexpr int kBBytes = BN * kKC * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int kOutBufs = 2;
+    static constexpr int kBarOff = kStages * kStage + kOutBufs * kStageBytes;
+    static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsConv, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+          const __grid_constant__ CUtensorMap map_out, const ConvParams p)
+{
+    using Plan = SmemPlan<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* out_stage = smem + Plan::kStages * Plan::kStage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Plan::kBarOff);
+    uint64_t* empty = full + Plan::kStages;
+    uint64_t* tfull = empty + Plan::kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / kKC;
+    const int ksteps = p.taps * kchunks;
+    constexpr uint32_t kTmemCols = 2 * BN >= 32 ? 2 * BN : 32;
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    }
+    if (warp == 5 && lane == 0) {
+        for (int s = 0; s < Plan::kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_holder, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles_n;
+                int rest = tile / p.n_tiles_n;
+                const int tw = rest % p.tiles_w; rest /= p.tiles_w;
+                const int th = rest % p.tiles_h;
+                const int img = rest / p.tiles_h;
+                const int h0 = th * kTileH, w0 = tw * kTileW, n0 = nt * BN;
+                const int pad = p.ksize / 2;
+                for (int ks = 0; ks < ksteps; ks++) {
+                    const int tap = ks / kchunks, c0 = (ks % kchunks) * kKC;
+                    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Plan::kStage;
+                    mbar_arrive_expect_tx(&full[stage], Plan::kStage);
+                    tma_load_4d(sa, &map_in, &full[stage], c0, w0 + dx, h0 + dy, img);
+                    tma_load_2d(sa + kABytes, &map_w, &full[stage], tap * p.Cin + c0, n0);
+                    if (++stage == Plan::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int ks = 0; ks < ksteps; ks++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Plan::kStage);
+                    const uint64_t da = make_desc(sa), db = make_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kKC / 16; k++)
+                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0);
+                    umma_commit(&empty[stage]);  // smem slot free once these MMAs have read it
+                    if (++stage == Plan::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);  // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue warps 0..3 =====================
+        int it = 0;
+        int obuf = 0;
+        const int row = warp * 32 + lane;  // pixel of the tile = TMEM lane
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            const int nt = tile % p.n_tiles_n;
+            int rest = tile / p.n_tiles_n;
+            const int tw = rest % p.tiles_w; rest /= p.tiles_w;
+            const int th = rest % p.tiles_h;
+            const int img = rest / p.tiles_h;
+            const int h0 = th * kTileH, w0 = tw * kTileW, n0 = nt * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int g = 0; g < BN / 64; g++) {
+                // staging buffer obuf must have been read out by the TMA store issued two groups ago
+                if (threadIdx.x == 0) tma_store_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint8_t* ob = out_stage + obuf * kStageBytes;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + g * 64 + half * 32, r);
+                    tmem_ld_wait();
+                    const float* bias = p.bias + n0 + g * 64 + half * 32;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {  // four 16-byte pieces = 8 channels each
+                        uint32_t packed[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float v0 = __uint_as_float(r[j * 8 + q * 2]) + __ldg(bias + j * 8 + q * 2);
+                            float v1 = __uint_as_float(r[j * 8 + q * 2 + 1]) + __ldg(bias + j * 8 + q * 2 + 1);
+                            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                            packed[q] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        const int piece = half * 4 + j;  // 16-byte piece index within the 128-byte row
+                        uint4* dst = reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4));
+                        *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 0) {
+                    tma_store_4d(&map_out, ob, n0 + g * 64, w0, h0, img);
+                    tma_store_commit();
+                }
+                obuf ^= 1;
+            }
+            // all TMEM reads of this accumulator stage are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1_1 (Cin = 3, K = 27: below any tensor-core tile) on the CUDA cores, fused with the input
+// pre-processing-free path: fp32 NHWC in, bf16 NHWC out, bias + ReLU.  One thread = one pixel x 16
+// output channels; the 27 x Cout weights sit in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int CO_PER_THREAD>
+__global__ void __launch_bounds__(256)
+k_conv_small_cin(const float* __restrict__ in, const float* __restrict__ w /*[3][3][Cin][Cout]*/,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin, int Cout,
+                 int relu)
+{
+    extern __shared__ float sw[];  // [9*Cin][Cout] + bias[Cout]
+    const int K = 9 * Cin;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[K * Cout + i] = bias[i];
+    __syncthreads();
+    const int groups = Cout / CO_PER_THREAD;
+    const size_t total = (size_t)B * H * W * groups;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const size_t pix = idx / groups;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H);
+        const size_t n = pix / ((size_t)W * H);
+        float acc[CO_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < CO_PER_THREAD; k++) acc[k] = sw[K * Cout + g * CO_PER_THREAD + k];
+        for (int r = 0; r < 3; r++) {
+            const int yy = y + r - 1;
+            if (yy < 0 || yy >= H) continue;
+            for (int s = 0; s < 3; s++) {
+                const int xx = x + s - 1;
+                if (xx < 0 || xx >= W) continue;
+                const float* ip = in + ((n * H + yy) * W + xx) * Cin;
+                for (int c = 0; c < Cin; c++) {
+                    const float v = __ldg(ip + c);
+                    const float* wp = sw + ((r * 3 + s) * Cin + c) * Cout + g * CO_PER_THREAD;
+#pragma unroll
+                    for (int k = 0; k < CO_PER_THREAD; k++) acc[k] = fmaf(v, wp[k], acc[k]);
+                }
+            }
+        }
+        __nv_bfloat16* op = out + pix * Cout + g * CO_PER_THREAD;
+#pragma unroll
+        for (int k = 0; k < CO_PER_THREAD; k += 2) {
+            float v0 = acc[k], v1 = acc[k + 1];
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            *reinterpret_cast<__nv_bfloat162*>(op + k) = __floats2bfloat162_rn(v0, v1);
+        }
+    }
+}
+
+// 2x2 / stride 2 max pool, NHWC bf16 (Network.max_pool, network.py:303-310; H, W even here)
+__global__ void __launch_bounds__(256)
+k_maxpool2x2_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C)
+{
+    const int Ho = H / 2, Wo = W / 2, cg = C / 8;
+    const size_t total = (size_t)B * Ho * Wo * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % cg);
+        size_t r = idx / cg;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho);
+        const size_t n = r / Ho;
+        const __nv_bfloat16* p0 = in + ((n * H + 2 * yo) * W + 2 * xo) * C + g * 8;
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(p0));
+        uint4 b = __ldg(reinterpret_cast<const uint4*>(p0 + C));
+        uint4 c = __ldg(reinterpret_cast<const uint4*>(p0 + (size_t)W * C));
+        uint4 d = __ldg(reinterpret_cast<const uint4*>(p0 + (size_t)W * C + C));
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+        const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
+        const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) po[k] = __hmax2(__hmax2(pa[k], pb[k]), __hmax2(pc[k], pd[k]));
+        *reinterpret_cast<uint4*>(out + ((n * Ho + yo) * Wo + xo) * C + g * 8) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_c)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return PCNN_E_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, kTileW, kTileH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(NHWC %dx%dx%dx%d) failed: %d", B, H, W, C, (int)r); return PCNN_E_CUDA; }
+    return PCNN_OK;
+}
+
+static int make_map_weights(CUtensorMap* m, const void* ptr, int K, int Cout, int bn)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return PCNN_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {kKC, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d) failed: %d", Cout, K, (int)r); return PCNN_E_CUDA; }
+    return PCNN_OK;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& mi, const CUtensorMap& mw, const CUtensorMap& mo, const ConvParams& p, int num_sms,
+                       cudaStream_t st)
+{
+    using Plan = SmemPlan<BN>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
+        if (e != cudaSuccess) { set_error("conv_tc<%d>: cannot reserve %d B of shared memory: %s", BN, Plan::kTotal, cudaGetErrorString(e)); return PCNN_E_CUDA; }
+        attr = true;
+    }
+    int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    k_conv_tc<BN><<<grid, kThreadsConv, Plan::kTotal, st>>>(mi, mw, mo, p);
+    return check_launch("conv_tc");
+}
+
+}  // namespace convtc
+}  // namespace pcnn
+
+using namespace pcnn;
+using namespace pcnn::convtc;
+
+// in [B,H,W,Cin] bf16, weights [Cout][ksize*ksize*Cin] bf16 (tap-major, channel-minor), bias [Cout] f32,
+// out [B,H,W,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0, ksize in {1, 3}.
+extern "C" int pcnn_conv_bf16_tc(const void* in, const void* weights, const float* bias, void* out, int B, int H, int W,
+                                 int Cin, int Cout, int ksize, int relu, int block_n, void* stream)
+{
+    PCNN_REQUIRE(in && weights && bias && out, "conv: NULL tensor pointer");
+    PCNN_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize must be 1 or 3 (got %d)", ksize);
+    PCNN_REQUIRE(Cin % 64 == 0 && Cin >= 64, "conv: Cin must be a multiple of 64 (got %d)", Cin);
+    PCNN_REQUIRE(Cout % 64 == 0 && Cout >= 64, "conv: Cout must be a multiple of 64 (got %d)", Cout);
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1, "conv: bad shape");
+    int bn = block_n;
+    if (bn == 0) bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    PCNN_REQUIRE((bn == 64 || bn == 128 || bn == 256) && Cout % bn == 0, "conv: block_n %d does not divide Cout %d", bn, Cout);
+    CUtensorMap mi, mw, mo;
+    int rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC);
+    if (rc) return rc;
+    rc = make_map_weights(&mw, weights, ksize * ksize * Cin, Cout, bn);
+    if (rc) return rc;
+    rc = make_map_nhwc(&mo, out, B, H, W, Cout, 64);
+    if (rc) return rc;
+    ConvParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.ksize = ksize; p.taps = ksize * ksize;
+    p.tiles_h = (H + kTileH - 1) / kTileH;
+    p.tiles_w = (W + kTileW - 1) / kTileW;
+    p.n_tiles_n = Cout / bn;
+    p.total_tiles = B * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    p.relu = relu;
+    p.bias = bias;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 256) return launch_conv<256>(mi, mw, mo, p, sms, st);
+    if (bn == 128) return launch_conv<128>(mi, mw, mo, p, sms, st);
+    return launch_conv<64>(mi, mw, mo, p, sms, st);
+}
+
+// conv with tiny Cin (conv1_1): in [B,H,W,Cin] f32, weights HWIO [3,3,Cin,Cout] f32, out [B,H,W,Cout] bf16
+extern "C" int pcnn_conv3x3_small_cin(const float* in, const float* weights_hwio, const float* bias, void* out, int B, int H,
+                                      int W, int Cin, int Cout, int relu, void* stream)
+{
+    PCNN_REQUIRE(in && weights_hwio && bias && out, "conv_small: NULL tensor pointer");
+    PCNN_REQUIRE(Cin >= 1 && Cin <= 8 && Cout % 16 == 0 && Cout <= 128, "conv_small: needs Cin <= 8, Cout %% 16 == 0, Cout <= 128");
+    size_t smem = sizeof(float) * (size_t)(9 * Cin + 1) * Cout;
+    size_t total = (size_t)B * H * W * (Cout / 16);
+    int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 8 ? (total + 255) / 256 : (size_t)kNumSMs * 8);
+    k_conv_small_cin<16><<<blocks, 256, smem, (cudaStream_t)stream>>>(in, weights_hwio, bias, (__nv_bfloat16*)out, B, H, W, Cin,
+                                                                      Cout, relu);
+    return check_launch("conv_small_cin");
+}
+
+extern "C" int pcnn_maxpool2x2_bf16(const void* in, void* out, int B, int H, int W, int C, void* stream)
+{
+    PCNN_REQUIRE(in && out, "maxpool: NULL tensor pointer");
+    PCNN_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool: needs even H, W and C %% 8 == 0 (got %d,%d,%d)", H, W, C);
+    size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+    k_maxpool2x2_bf16<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, H, W, C);
+    return check_launch("maxpool2x2");
+}

@@ -1,0 +1,60 @@
+"""tcgen05 implicit-GEMM convolution vs a plain PyTorch fp32 reference of the same op
+(tf.nn.conv2d semantics of lib/networks/network.py:159-188: NHWC x HWIO, SAME, stride 1, bias, ReLU).
+Inputs and weights are rounded to bf16 first, so only the fp32 accumulation order and the final
+bf16 rounding of the output differ: tolerance = 2 bf16 ulps of the output magnitude."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x_bf16, w_hwio_bf16, bias, relu):
+    x = x_bf16.float().permute(0, 3, 1, 2)
+    w = w_hwio_bf16.float().permute(3, 2, 0, 1)
+    y = F.conv2d(x, w, bias, padding=w.shape[2] // 2)
+    if relu:
+        y = F.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,bn", [
+    (1, 8, 16, 64, 64, 3, 64),       # exactly one tile
+    (2, 24, 48, 64, 64, 3, 64),      # conv1_2-like
+    (1, 30, 40, 128, 128, 3, 128),   # ragged tiles (30 = 3*8+6, 40 = 2*16+8): zero-fill + clipped stores
+    (2, 16, 32, 256, 256, 3, 256),
+    (1, 15, 20, 512, 512, 3, 256),   # two N tiles
+    (1, 16, 32, 128, 256, 3, 128),
+    (2, 16, 16, 512, 128, 1, 128),   # 1x1 head
+    (3, 37, 53, 64, 128, 3, 0),      # odd sizes, automatic N tile
+])
+def test_conv_tc_matches_fp32_reference(cuda, B, H, W, Cin, Cout, k, bn):
+    from posecnn_b200 import conv
+    g = torch.Generator(device="cpu").manual_seed(1234 + H + Cin)
+    x = torch.randn((B, H, W, Cin), generator=g).to(torch.bfloat16).to(cuda)
+    w = (torch.randn((k, k, Cin, Cout), generator=g) * (2.0 / (k * k * Cin)) ** 0.5).to(torch.bfloat16).to(cuda)
+    bias = torch.randn((Cout,), generator=g).to(cuda)
+    for relu in (True, False):
+        y = conv.conv_bf16(x, conv.hwio_to_tc(w.float()), bias, k, relu, bn)
+        torch.cuda.synchronize()
+        want = ref_conv(x, w, bias, relu)
+        err = (y.float() - want).abs()
+        tol = 2 ** -7 * want.abs().clamp(min=1.0)          # 2 bf16 ulps
+        assert (err <= tol).all(), f"max err {err.max().item():.4g} at |want| up to {want.abs().max().item():.3g}"
+        rel_l2 = (err.pow(2).sum() / want.pow(2).sum()).sqrt().item()
+        assert rel_l2 < 4e-3, rel_l2
+
+
+def test_conv_small_cin_and_maxpool(cuda):
+    from posecnn_b200 import conv
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn((2, 20, 28, 3), generator=g).to(cuda)
+    w = (torch.randn((3, 3, 3, 64), generator=g) * 0.3).to(cuda)
+    b = torch.randn((64,), generator=g).to(cuda)
+    y = conv.conv3x3_small_cin(x, w, b, True)
+    want = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1)).permute(0, 2, 3, 1)
+    assert ((y.float() - want).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()
+    p = conv.maxpool2x2(y)
+    wantp = F.max_pool2d(y.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(p.float(), wantp)
