@@ -153,7 +153,29 @@ int pcnn_conv_bf16_tc(const void* in_bf16, const void* weights_bf16, const float
 /* conv1_1 (Cin = 3): in [B,H,W,Cin] f32, weights HWIO [3,3,Cin,Cout] f32 -> out [B,H,W,Cout] bf16 */
 int pcnn_conv3x3_small_cin(const float* in, const float* weights_hwio, const float* bias, void* out_bf16, int B,
                            int H, int W, int Cin, int Cout, int relu, void* stream);
+/* first layer on the tensor cores: im2col [B,H,W,3] (f32, or u8 minus per-channel mean: the BGR - PIXEL_MEANS
+ * pre-processing of lib/fcn/test.py:37-110 fused) -> [B,H,W,64] bf16 with K = tap*3 + c, then a 1x1 pcnn_conv_bf16_tc */
+int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_host, void* out_bf16, int B, int H, int W,
+                   void* stream);
 int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * FCN heads after the 1x1 convolutions on conv4_3 / conv5_3 (networks/vgg16_convs.py:128-163):
+ * add + fixed-bilinear conv2d_transpose (networks/network.py:141-157, 207-222) + `score` /
+ * `vertex_pred` 1x1 + softmax / arg-max.  The bilinear up-sampling commutes with the 1x1
+ * convolutions, so the matrices are applied at 1/8 resolution (pcnn_lowres_heads) and one
+ * streaming kernel (pcnn_up8_heads) produces label_2d [B,H,W] int32, vertex_pred [B,H,W,3C] f32
+ * and (optional) prob_normalized / score [B,H,W,C] f32.
+ *   score4/vert4 [B,h,w,Cs|Cv] bf16 (1x1 convs of conv4_3), score5/vert5 [B,h/2,w/2,Cs|Cv] bf16,
+ *   w_score [Cs][C] f32, w_vertex [Cv][3C] f32, lowres [B,h,w,4C] f32, H = 8h, W = 8w.
+ */
+int pcnn_lowres_heads(const void* score4, const void* score5, const void* vert4, const void* vert5,
+                      const float* w_score, const float* w_vertex, int B, int h, int w, int Cs, int Cv, int C,
+                      float* lowres, void* stream);
+int pcnn_up8_heads(const float* lowres, const float* bias_score, const float* bias_vertex, int B, int h, int w,
+                   int C, int32_t* label, float* vertex, float* prob, float* score, void* stream);
+/* depthwise bilinear conv2d_transpose (k x k, stride s, SAME) on f32 NHWC — un-fused reference path */
+int pcnn_deconv_bilinear(const float* in, float* out, int B, int h, int w, int C, int k, int s, void* stream);
 
 #ifdef __cplusplus
 }

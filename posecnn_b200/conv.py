@@ -45,3 +45,22 @@ def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, H // 2, W // 2, C), dtype=torch.bfloat16, device=x.device)
     check(lib().pcnn_maxpool2x2_bf16(ptr(x), ptr(out), B, H, W, C, stream()))
     return out
+
+
+def im2col_c3(x: torch.Tensor, mean=None) -> torch.Tensor:
+    """First layer: x [B,H,W,3] f32 or u8 -> [B,H,W,64] bf16 (K = tap*3 + c, zero padded to 64)."""
+    import ctypes
+    assert x.is_cuda and x.is_contiguous() and x.shape[3] == 3 and x.dtype in (torch.float32, torch.uint8)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=x.device)
+    m = (ctypes.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+    check(lib().pcnn_im2col_c3(ptr(x), int(x.dtype == torch.uint8), m, ptr(out), B, H, W, stream()))
+    return out
+
+
+def conv1_1_weights_to_tc(w_hwio: torch.Tensor) -> torch.Tensor:
+    """[3,3,3,Cout] f32 -> [Cout, 64] bf16 matching im2col_c3's K order (tap*3 + c)."""
+    co = w_hwio.shape[3]
+    w = torch.zeros((co, 64), dtype=torch.float32, device=w_hwio.device)
+    w[:, :27] = w_hwio.reshape(27, co).t()
+    return w.to(torch.bfloat16).contiguous()

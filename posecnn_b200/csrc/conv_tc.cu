@@ -393,6 +393,38 @@ k_conv_small_cin(const float* __restrict__ in, const float* __restrict__ w /*[3]
     }
 }
 
+// im2col for the first layer only (Cin = 3, K = 27 < one UMMA K step): [B,H,W,3] -> [B,H,W,64] bf16 with
+// K index = tap * 3 + c (zero beyond 27), so conv1_1 runs on the tensor cores as a 1x1 convolution.
+// The input pre-processing of the caller (lib/fcn/test.py:37-110: BGR - PIXEL_MEANS) is fused for uint8
+// input: value = (float)u8 - mean[c].
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+k_im2col_c3(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, float m0, float m1, float m2)
+{
+    const size_t total = (size_t)B * H * W * 8;
+    const float mean[3] = {m0, m1, m2};
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx & 7);
+        const size_t pix = idx >> 3;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H);
+        const size_t n = pix / ((size_t)W * H);
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int k = j * 8 + e;
+            float val = 0.f;
+            if (k < 27) {
+                const int tap = k / 3, c = k % 3;
+                const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                    val = (float)in[((n * H + yy) * W + xx) * 3 + c] - mean[c];
+            }
+            v[e] = __float2bfloat16_rn(val);
+        }
+        *reinterpret_cast<uint4*>(out + pix * 64 + j * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 // 2x2 / stride 2 max pool, NHWC bf16 (Network.max_pool, network.py:303-310; H, W even here)
 __global__ void __launch_bounds__(256)
 k_maxpool2x2_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C)
@@ -554,4 +586,21 @@ extern "C" int pcnn_maxpool2x2_bf16(const void* in, void* out, int B, int H, int
     int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
     k_maxpool2x2_bf16<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, H, W, C);
     return check_launch("maxpool2x2");
+}
+
+// first-layer im2col: in [B,H,W,3] (f32, or u8 with the per-channel mean subtracted) -> out [B,H,W,64] bf16
+extern "C" int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_host, void* out_bf16, int B, int H, int W,
+                              void* stream)
+{
+    PCNN_REQUIRE(in && out_bf16, "im2col: NULL tensor pointer");
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    if (mean3_host) { m0 = mean3_host[0]; m1 = mean3_host[1]; m2 = mean3_host[2]; }
+    size_t total = (size_t)B * H * W * 8;
+    int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_is_u8)
+        k_im2col_c3<unsigned char><<<blocks, 256, 0, st>>>((const unsigned char*)in, (__nv_bfloat16*)out_bf16, B, H, W, m0, m1, m2);
+    else
+        k_im2col_c3<float><<<blocks, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out_bf16, B, H, W, m0, m1, m2);
+    return check_launch("im2col_c3");
 }

@@ -1,0 +1,248 @@
+// heads.cu — the FCN heads of vgg16_convs after the 1x1 convolutions on conv4_3 / conv5_3:
+// semantic-label head and vertex head (lib/networks/vgg16_convs.py:128-163).
+//
+// The reference runs, at FULL resolution, two dense conv2d_transpose ops whose filters are fixed
+// diagonal bilinear kernels (make_deconv_filter, lib/networks/network.py:141-157, 207-222) followed by
+// 1x1 convolutions (`score` 64->C with ReLU, `vertex_pred` 128->3C): 50 GFLOP/frame of multiplications
+// by zero plus 6 GFLOP of 1x1 work on 307 200 pixels.  Both stages are linear and act on different
+// axes (bilinear: per channel over space; 1x1: per pixel over channels), so they commute:
+//
+//      conv1x1(up8(x)) + b  ==  up8(conv1x1_nobias(x)) + b
+//
+// (the bias must stay outside: near the image border the transposed convolution's weights do not sum
+// to one).  Hence:
+//   k_lowres_heads  at 1/8 resolution: add_score = score_conv4 + up2(score_conv5) (both heads), then
+//                   the two 1x1 matrices -> [B,h,w, C + 3C] fp32
+//   k_up8_heads     per output pixel: bilinear x8 (exact conv2d_transpose weights), + bias, ReLU /
+//                   softmax / arg-max for the label head, + bias for the vertex head; one streaming
+//                   pass that writes label_2d (int32), vertex_pred (fp32) and optionally the
+//                   normalised probabilities.
+#include <cuda_bf16.h>
+#include <float.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pcnn {
+
+// make_deconv_filter (network.py:141-157): f = ceil(k/2), c = (2f - 1 - f%2) / (2f), W[x] = 1 - |x/f - c|
+__host__ __device__ inline float deconv_w(int x, int k)
+{
+    int f = (k + 1) / 2;
+    float c = (2.f * f - 1.f - (float)(f % 2)) / (2.f * f);
+    return 1.f - fabsf((float)x / (float)f - c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_lowres_heads: 8 low-resolution pixels per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int kLrPix = 8;
+
+__global__ void __launch_bounds__(256)
+k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_bfloat16* __restrict__ s5 /*[B,h/2,w/2,Cs]*/,
+               const __nv_bfloat16* __restrict__ v4 /*[B,h,w,Cv]*/, const __nv_bfloat16* __restrict__ v5,
+               const float* __restrict__ Ws /*[Cs][C]*/, const float* __restrict__ Wv /*[Cv][3C]*/, int B, int h, int w,
+               int Cs, int Cv, int C, float* __restrict__ out /*[B,h,w,4C]*/)
+{
+    extern __shared__ float sm[];
+    const int Ct = Cs + Cv;        // channels of the two "add" tensors
+    const int No = 4 * C;          // outputs per pixel
+    float* sW = sm;                // [Cs*C + Cv*3C]
+    float* sx = sm + Cs * C + Cv * 3 * C;  // [kLrPix][Ct]
+    for (int i = threadIdx.x; i < Cs * C; i += blockDim.x) sW[i] = Ws[i];
+    for (int i = threadIdx.x; i < Cv * 3 * C; i += blockDim.x) sW[Cs * C + i] = Wv[i];
+    const size_t npix = (size_t)B * h * w;
+    const int h5 = h / 2, w5 = w / 2;
+    for (size_t p0 = (size_t)blockIdx.x * kLrPix; p0 < npix; p0 += (size_t)gridDim.x * kLrPix) {
+        __syncthreads();
+        // add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
+        for (int i = threadIdx.x; i < kLrPix * Ct; i += blockDim.x) {
+            const int pi = i / Ct, ch = i % Ct;
+            const size_t p = p0 + pi;
+            float val = 0.f;
+            if (p < npix) {
+                const int x = (int)(p % w), y = (int)((p / w) % h);
+                const size_t n = p / ((size_t)w * h);
+                const bool vert = ch >= Cs;
+                const int cc = vert ? ch - Cs : ch, Cn = vert ? Cv : Cs;
+                const __nv_bfloat16* a = vert ? v4 : s4;
+                const __nv_bfloat16* b5 = vert ? v5 : s5;
+                val = __bfloat162float(a[p * Cn + cc]);
+                // out[o] += in[i] * W[o - 2 i + 1], 0 <= o - 2i + 1 <= 3
+                const int iy0 = ((y + 1) >> 1) - 1, ix0 = ((x + 1) >> 1) - 1;
+                float up = 0.f;
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++) {
+                    const int iy = iy0 + dy, ky = y - 2 * iy + 1;
+                    if (iy < 0 || iy >= h5 || ky < 0 || ky > 3) continue;
+#pragma unroll
+                    for (int dx = 0; dx < 2; dx++) {
+                        const int ix = ix0 + dx, kx = x - 2 * ix + 1;
+                        if (ix < 0 || ix >= w5 || kx < 0 || kx > 3) continue;
+                        up += deconv_w(ky, 4) * deconv_w(kx, 4) * __bfloat162float(b5[((n * h5 + iy) * w5 + ix) * Cn + cc]);
+                    }
+                }
+                val += up;
+            }
+            sx[i] = val;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kLrPix * No; i += blockDim.x) {
+            const int pi = i / No, o = i % No;
+            const size_t p = p0 + pi;
+            if (p >= npix) continue;
+            float acc = 0.f;
+            if (o < C) {
+                const float* x = sx + pi * Ct;
+                for (int k = 0; k < Cs; k++) acc = fmaf(x[k], sW[k * C + o], acc);
+            } else {
+                const float* x = sx + pi * Ct + Cs;
+                const float* wv = sW + Cs * C + (o - C);
+                for (int k = 0; k < Cv; k++) acc = fmaf(x[k], wv[k * 3 * C], acc);
+            }
+            out[p * No + o] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_up8_heads: one warp per output pixel (lanes over channels)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/,
+            const float* __restrict__ bias_v /*[3C]*/, int B, int h, int w, int C, int* __restrict__ label /*[B,8h,8w]*/,
+            float* __restrict__ vertex /*[B,8h,8w,3C]*/, float* __restrict__ prob /*[B,8h,8w,C] or null*/,
+            float* __restrict__ score_out /*[B,8h,8w,C] or null*/)
+{
+    const int lane = threadIdx.x & 31;
+    const int H = 8 * h, W = 8 * w, No = 4 * C;
+    const size_t npix = (size_t)B * H * W;
+    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int rounds = (No + 31) / 32;
+    for (size_t p = warp0; p < npix; p += nwarps) {
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        const size_t n = p / ((size_t)W * H);
+        // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
+        const int my = y >> 3, ty = y & 7, mx = x >> 3, tx = x & 7;
+        const int iy0 = ty < 4 ? my - 1 : my, ix0 = tx < 4 ? mx - 1 : mx;
+        float wy[2], wx[2];
+        int iy[2], ix[2];
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            iy[d] = iy0 + d; ix[d] = ix0 + d;
+            wy[d] = (iy[d] >= 0 && iy[d] < h) ? deconv_w(y - 8 * iy[d] + 4, 16) : 0.f;
+            wx[d] = (ix[d] >= 0 && ix[d] < w) ? deconv_w(x - 8 * ix[d] + 4, 16) : 0.f;
+            iy[d] = min(max(iy[d], 0), h - 1); ix[d] = min(max(ix[d], 0), w - 1);
+        }
+        const float* base = lr + n * (size_t)h * w * No;
+        const float* p00 = base + ((size_t)iy[0] * w + ix[0]) * No;
+        const float* p01 = base + ((size_t)iy[0] * w + ix[1]) * No;
+        const float* p10 = base + ((size_t)iy[1] * w + ix[0]) * No;
+        const float* p11 = base + ((size_t)iy[1] * w + ix[1]) * No;
+        const float w00 = wy[0] * wx[0], w01 = wy[0] * wx[1], w10 = wy[1] * wx[0], w11 = wy[1] * wx[1];
+        float sc = -FLT_MAX;  // this lane's class score (lanes < C), first round only when C <= 32
+        for (int r = 0; r < rounds; r++) {
+            const int ch = r * 32 + lane;
+            if (ch >= No) break;
+            // same accumulation order as a (ky, kx) loop of the transposed convolution
+            float v = w00 * __ldg(p00 + ch);
+            v = fmaf(w01, __ldg(p01 + ch), v);
+            v = fmaf(w10, __ldg(p10 + ch), v);
+            v = fmaf(w11, __ldg(p11 + ch), v);
+            if (ch < C) {
+                v = fmaxf(v + __ldg(bias_s + ch), 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
+                sc = v;
+                if (score_out) score_out[p * C + ch] = v;
+            } else {
+                vertex[p * 3 * C + (ch - C)] = v + __ldg(bias_v + ch - C);
+            }
+        }
+        // arg-max over classes, lowest index wins ties (tf.argmax); softmax for prob_normalized
+        float best = sc;
+        int bi = lane < C ? lane : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) label[p] = bi;
+        if (prob) {
+            float e = lane < C ? expf(sc - best) : 0.f;  // softmax_high_dimension, network.py:474-488
+            float s = e;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane < C) prob[p * C + lane] = e / s;
+        }
+    }
+}
+
+// generic bilinear transposed convolution (depthwise, diagonal filter): out[B,s*h,s*w,C] f32 from in[B,h,w,C] f32.
+// Only used by tests / the un-fused reference path.
+__global__ void __launch_bounds__(256)
+k_deconv_bilinear(const float* __restrict__ in, float* __restrict__ out, int B, int h, int w, int C, int k, int s)
+{
+    const int H = h * s, W = w * s, pad = (k - s) / 2;
+    const size_t total = (size_t)B * H * W * C;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        size_t r = idx / C;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const size_t n = r / H;
+        float acc = 0.f;
+        for (int iy = 0; iy < h; iy++) {
+            int ky = y - s * iy + pad;
+            if (ky < 0 || ky >= k) continue;
+            for (int ix = 0; ix < w; ix++) {
+                int kx = x - s * ix + pad;
+                if (kx < 0 || kx >= k) continue;
+                acc += deconv_w(ky, k) * deconv_w(kx, k) * in[((n * h + iy) * w + ix) * C + c];
+            }
+        }
+        out[idx] = acc;
+    }
+}
+
+}  // namespace pcnn
+
+using namespace pcnn;
+
+extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const void* vert4, const void* vert5,
+                                 const float* w_score, const float* w_vertex, int B, int h, int w, int Cs, int Cv, int C,
+                                 float* out, void* stream)
+{
+    PCNN_REQUIRE(score4 && score5 && vert4 && vert5 && w_score && w_vertex && out, "lowres_heads: NULL tensor pointer");
+    PCNN_REQUIRE(h % 2 == 0 && w % 2 == 0, "lowres_heads: conv4 resolution must be even (got %d x %d)", h, w);
+    size_t smem = sizeof(float) * ((size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrPix * (Cs + Cv));
+    PCNN_REQUIRE(smem <= 200 * 1024, "lowres_heads: weights do not fit shared memory");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_lowres_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    size_t npix = (size_t)B * h * w;
+    int blocks = (int)std::min<size_t>((npix + kLrPix - 1) / kLrPix, (size_t)kNumSMs * 4);
+    k_lowres_heads<<<blocks, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)score4, (const __nv_bfloat16*)score5,
+                                                               (const __nv_bfloat16*)vert4, (const __nv_bfloat16*)vert5, w_score,
+                                                               w_vertex, B, h, w, Cs, Cv, C, out);
+    return check_launch("lowres_heads");
+}
+
+extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, const float* bias_vertex, int B, int h, int w, int C,
+                              int32_t* label, float* vertex, float* prob, float* score, void* stream)
+{
+    PCNN_REQUIRE(lowres && bias_score && bias_vertex && label && vertex, "up8_heads: NULL tensor pointer");
+    PCNN_REQUIRE(C >= 1 && C <= 32, "up8_heads: 1 <= num_classes <= 32 (got %d)", C);
+    size_t npix = (size_t)B * h * w * 64;
+    int blocks = (int)std::min<size_t>((npix + 7) / 8, (size_t)kNumSMs * 32);
+    k_up8_heads<<<blocks, 256, 0, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, B, h, w, C, label, vertex, prob, score);
+    return check_launch("up8_heads");
+}
+
+extern "C" int pcnn_deconv_bilinear(const float* in, float* out, int B, int h, int w, int C, int k, int s, void* stream)
+{
+    PCNN_REQUIRE(in && out && k >= s && (k - s) % 2 == 0, "deconv_bilinear: bad arguments");
+    size_t total = (size_t)B * h * s * w * s * C;
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 16);
+    k_deconv_bilinear<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, B, h, w, C, k, s);
+    return check_launch("deconv_bilinear");
+}

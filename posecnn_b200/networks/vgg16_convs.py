@@ -1,0 +1,200 @@
+"""vgg16_convs — the PoseCNN network of lib/networks/vgg16_convs.py on the B200-native kernels.
+
+Mirrors the reference class (constructor arguments, layer names, parameter names `<layer>/weights`,
+`<layer>/biases` in TF layouts: conv HWIO, fc [in, out]) so that a TF1 checkpoint / VGG16 .npy
+dictionary (lib/networks/network.py:71-107) maps one to one.  The graph of
+vgg16_convs.setup() (vgg16_convs.py:79-212) is executed eagerly on one CUDA stream:
+
+    conv1_1 .. conv5_3 (+ _p trunk for RGBD)   tcgen05 implicit GEMM, bf16 x bf16 -> fp32   csrc/conv_tc.cu
+    score / vertex heads                         1x1 on tcgen05 + fused bilinear/softmax     csrc/heads.cu
+    hough_voting_gpu                             csrc/hough_vote.cu
+    roi_pool x2, add, fc6-fc8, tanh              csrc/pixel_ops.cu + cuBLAS (plain library GEMMs)
+
+PyTorch supplies device memory, streams and the three fully connected GEMMs only.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import conv
+from .._lib import check, lib, ptr, stream
+from ..hough_voting_gpu_layer import hough_voting_gpu_op
+from ..roi_pooling_layer import roi_pooling_op
+
+PIXEL_MEANS = (102.9801, 115.9465, 122.7717)  # lib/fcn/config.py:242 (BGR)
+
+VGG_CFG = [("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool1", ("conv2_1", 64, 128), ("conv2_2", 128, 128), "pool2",
+           ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), "pool3", ("conv4_1", 256, 512),
+           ("conv4_2", 512, 512), ("conv4_3", 512, 512), "pool4", ("conv5_1", 512, 512), ("conv5_2", 512, 512),
+           ("conv5_3", 512, 512)]
+
+
+class vgg16_convs:
+    def __init__(self, input_format="COLOR", num_classes=22, num_units=64, scales=(1.0,), threshold_label=1.0,
+                 vote_threshold=-1.0, vertex_reg_2d=True, vertex_reg_3d=False, pose_reg=True, adaptation=False,
+                 trainable=True, is_train=False, device="cuda"):
+        self.input_format = input_format
+        self.num_classes = num_classes
+        self.num_units = num_units
+        self.threshold_label = threshold_label
+        self.vertex_reg = vertex_reg_2d or vertex_reg_3d
+        self.vertex_reg_2d = vertex_reg_2d
+        self.pose_reg = pose_reg
+        # vgg16_convs.py:18-29
+        self.is_train = 1 if is_train else 0
+        self.skip_pixels = 10
+        self.vote_threshold = vote_threshold
+        self.vote_percentage = 0.02
+        self.device = torch.device(device)
+        self.params: dict[str, torch.Tensor] = {}
+        self._tc: dict[str, torch.Tensor] = {}
+        self.layers: dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ parameters
+    def param_shapes(self):
+        C, U = self.num_classes, self.num_units
+        shapes = {}
+        trunks = [""] + (["_p"] if self.input_format == "RGBD" else [])
+        for sfx in trunks:
+            for item in VGG_CFG:
+                if isinstance(item, tuple):
+                    name, ci, co = item
+                    shapes[f"{name}{sfx}/weights"] = (3, 3, ci, co)
+                    shapes[f"{name}{sfx}/biases"] = (co,)
+        cin_head = 1024 if self.input_format == "RGBD" else 512
+        for name, co in (("score_conv5", U), ("score_conv4", U), ("score_conv5_vertex", 128), ("score_conv4_vertex", 128)):
+            shapes[f"{name}/weights"] = (1, 1, cin_head if not name.endswith("vertex") else 512, co)
+            shapes[f"{name}/biases"] = (co,)
+        shapes["score/weights"] = (1, 1, U, C); shapes["score/biases"] = (C,)
+        shapes["vertex_pred/weights"] = (1, 1, 128, 3 * C); shapes["vertex_pred/biases"] = (3 * C,)
+        shapes["fc6/weights"] = (7 * 7 * 512, 4096); shapes["fc6/biases"] = (4096,)
+        shapes["fc7/weights"] = (4096, 4096); shapes["fc7/biases"] = (4096,)
+        shapes["fc8/weights"] = (4096, 4 * C); shapes["fc8/biases"] = (4 * C,)
+        return shapes
+
+    def init_random(self, seed=0, bias_std=0.0):
+        """Seeded Kaiming-normal init (fan-in, gain sqrt 2), biases 0 — NOT the reference's
+        truncated_normal(0.001), which makes the net output background only (SURVEY finding 10)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name, shp in self.param_shapes().items():
+            if name.endswith("weights"):
+                fan_in = int(np.prod(shp[:-1]))
+                t = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)
+            else:
+                t = torch.randn(shp, generator=g) * bias_std if bias_std > 0 else torch.zeros(shp)
+            self.params[name] = t.to(self.device)
+        self.prepare()
+        return self
+
+    def load(self, data_dict: dict):
+        """TF-name dictionary {layer: {'weights': ..., 'biases': ...}} (VGG16 .npy, network.py:71-107) or flat
+        {'layer/weights': ...}."""
+        for k, v in data_dict.items():
+            if isinstance(v, dict):
+                for kk, vv in v.items():
+                    self.params[f"{k}/{kk}"] = torch.as_tensor(np.asarray(vv), dtype=torch.float32, device=self.device)
+                    if self.input_format == "RGBD" and k.startswith("conv") and "score" not in k:
+                        self.params[f"{k}_p/{kk}"] = self.params[f"{k}/{kk}"].clone()  # '_p' duplicate scopes, network.py:88-95
+            else:
+                self.params[k] = torch.as_tensor(np.asarray(v), dtype=torch.float32, device=self.device)
+        self.prepare()
+        return self
+
+    def prepare(self):
+        """Derive the tensor-core weight layouts once ([Cout][k*k*Cin] bf16)."""
+        P, T = self.params, self._tc
+        T.clear()
+        for name, shp in self.param_shapes().items():
+            if not name.endswith("weights") or name.startswith("fc") or name in ("score/weights", "vertex_pred/weights"):
+                continue
+            w = P[name]
+            if w.shape[2] == 3:  # conv1_1: im2col K order
+                T[name] = conv.conv1_1_weights_to_tc(w)
+            else:
+                T[name] = conv.hwio_to_tc(w)
+        for name in ("fc6", "fc7", "fc8"):
+            T[f"{name}/weights"] = P[f"{name}/weights"].t().contiguous().to(torch.bfloat16)  # [out, in] for F.linear
+        T["score/w"] = P["score/weights"].reshape(self.num_units, self.num_classes).contiguous()
+        T["vertex_pred/w"] = P["vertex_pred/weights"].reshape(128, 3 * self.num_classes).contiguous()
+
+    # ------------------------------------------------------------------ graph pieces
+    def _trunk(self, data, sfx=""):
+        """13 x (conv3x3 + bias + ReLU), 4 x max-pool (vgg16_convs.py:80-97).  data: [B,H,W,3] u8 (BGR, mean
+        subtracted on the fly) or f32 (already pre-processed)."""
+        P, T = self.params, self._tc
+        mean = PIXEL_MEANS if data.dtype == torch.uint8 else None
+        x = conv.im2col_c3(data, mean)
+        x = conv.conv_bf16(x, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], 1, True)
+        feats = {}
+        for item in VGG_CFG[1:]:
+            if isinstance(item, str):
+                x = conv.maxpool2x2(x)
+            else:
+                name = item[0]
+                x = conv.conv_bf16(x, T[f"{name}{sfx}/weights"], P[f"{name}{sfx}/biases"], 3, True)
+                if name in ("conv4_3", "conv5_3"):
+                    feats[name] = x
+        return feats
+
+    def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True):
+        """Inference / forward pass.  data [B,H,W,3] (u8 BGR or pre-processed f32), H, W multiples of 16
+        (pad_im, lib/utils/blob.py:48-58).  Returns self.layers with the reference's layer names."""
+        C = self.num_classes
+        L = self.layers = {}
+        P, T = self.params, self._tc
+        B, H, W, _ = data.shape
+        assert H % 16 == 0 and W % 16 == 0, "pad the image to a multiple of 16 (lib/utils/blob.py:48-58)"
+        f = self._trunk(data)
+        c4, c5 = f["conv4_3"], f["conv5_3"]
+        L["conv4_3"], L["conv5_3"] = c4, c5
+        if self.input_format == "RGBD":
+            fp = self._trunk(data_p, "_p")
+            h4, h5 = torch.cat([c4, fp["conv4_3"]], 3), torch.cat([c5, fp["conv5_3"]], 3)  # concat_conv4/5
+        else:
+            h4, h5 = c4, c5
+        # 1x1 convolutions on the tensor cores (score_conv4/5 have a ReLU, the vertex ones do not)
+        s5 = conv.conv_bf16(h5, T["score_conv5/weights"], P["score_conv5/biases"], 1, True)
+        s4 = conv.conv_bf16(h4, T["score_conv4/weights"], P["score_conv4/biases"], 1, True)
+        v5 = conv.conv_bf16(c5, T["score_conv5_vertex/weights"], P["score_conv5_vertex/biases"], 1, False)
+        v4 = conv.conv_bf16(c4, T["score_conv4_vertex/weights"], P["score_conv4_vertex/biases"], 1, False)
+        L["score_conv4"], L["score_conv5"], L["score_conv4_vertex"], L["score_conv5_vertex"] = s4, s5, v4, v5
+        h, w = H // 8, W // 8
+        lowres = torch.empty((B, h, w, 4 * C), dtype=torch.float32, device=data.device)
+        check(lib().pcnn_lowres_heads(ptr(s4), ptr(s5), ptr(v4), ptr(v5), ptr(T["score/w"]), ptr(T["vertex_pred/w"]), B, h, w,
+                                      self.num_units, 128, C, ptr(lowres), stream()))
+        label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
+        vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
+        prob = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_prob else None
+        check(lib().pcnn_up8_heads(ptr(lowres), ptr(P["score/biases"]), ptr(P["vertex_pred/biases"]), B, h, w, C, ptr(label),
+                                   ptr(vertex), ptr(prob), ptr(None), stream()))
+        L["label_2d"], L["vertex_pred"] = label, vertex
+        if want_prob:
+            L["prob_normalized"] = prob
+        if not self.vertex_reg_2d:
+            return L
+        box, pose, target, weight, domain, num_rois, status = hough_voting_gpu_op.hough_voting_gpu_capacity(
+            label, vertex, extents, meta_data, poses, self.is_train, self.vote_threshold, self.vote_percentage, self.skip_pixels)
+        # fixed-shape pose head over the ROI capacity of this batch size (rows beyond num_rois are all-zero ROIs)
+        cap_rows = max(1, min(box.shape[0], (128 // B) * B * (9 if self.is_train else 1)))
+        rois = box[:cap_rows]
+        L["rois_capacity"], L["num_rois"] = rois, num_rois
+        L["poses_init"], L["poses_target"], L["poses_weight"] = pose[:cap_rows], target[:cap_rows], weight[:cap_rows]
+        if self.pose_reg:
+            p5, _ = roi_pooling_op.roi_pool(c5.float(), rois, 7, 7, 1.0 / 16.0, 0)
+            p4, _ = roi_pooling_op.roi_pool(c4.float(), rois, 7, 7, 1.0 / 8.0, 0)
+            x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                     # pool_score, flatten (h, w, c)
+            x = torch.relu(torch.nn.functional.linear(x, T["fc6/weights"], P["fc6/biases"].to(torch.bfloat16)))
+            x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], P["fc7/biases"].to(torch.bfloat16)))
+            x = torch.nn.functional.linear(x, T["fc8/weights"], P["fc8/biases"].to(torch.bfloat16)).float()
+            L["poses_tanh"] = torch.tanh(x)
+        if sync_rois:
+            n = max(1, int(num_rois.item()))  # the one host read the op's data-dependent shape requires
+            L["rois"] = rois[:n]
+            for k in ("poses_init", "poses_target", "poses_weight"):
+                L[k] = L[k][:n]
+            if self.pose_reg:
+                L["poses_tanh"] = L["poses_tanh"][:n]
+        return L

@@ -8,6 +8,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def ref_conv(x_bf16, w_hwio_bf16, bias, relu):

@@ -1,0 +1,97 @@
+"""Network-level parity: the B200 pipeline (posecnn_b200.networks.vgg16_convs) against a plain PyTorch fp32
+restatement of the reference graph (tests/ref_network.py), stage by stage, on a small synthetic image.
+Precision: the trunk computes in BF16 x BF16 -> FP32; stated tolerance rel-L2 <= 2e-2 per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from posecnn_b200 import synth
+from tests import ref_network as R
+from tests.util import to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return ((a - b).pow(2).sum() / b.pow(2).sum().clamp(min=1e-30)).sqrt().item()
+
+
+@pytest.fixture(scope="module")
+def net_and_out(cuda):
+    from posecnn_b200.networks.vgg16_convs import vgg16_convs
+    net = vgg16_convs(num_classes=6, device=cuda).init_random(seed=0, bias_std=0.05)
+    rgb, _ = synth.make_images(2, 64, 96, seed=3)
+    data = torch.from_numpy(rgb).to(cuda)
+    meta = torch.from_numpy(np.stack([synth.make_meta(synth.intrinsics(64, 96))] * 2)).to(cuda)
+    ext = torch.from_numpy(synth.extents_for(6)).to(cuda)
+    out = dict(net.forward(data, meta, ext, want_prob=True))
+    torch.cuda.synchronize()
+    return net, data, meta, ext, out
+
+
+def test_trunk_features(net_and_out):
+    net, data, meta, ext, out = net_and_out
+    x = (data.float() - torch.tensor([102.9801, 115.9465, 122.7717], device=data.device)).permute(0, 3, 1, 2)
+    feats = R.trunk(net.params, x)
+    for name in ("conv4_3", "conv5_3"):
+        got = out[name].float().permute(0, 3, 1, 2)
+        e = rel_l2(got, feats[name])
+        assert e < 2e-2, (name, e)
+
+
+def test_heads_commuted_upsampling(net_and_out):
+    """Given the SAME 1x1-conv inputs, the fused heads (1x1 at 1/8 resolution, then bilinear x8 + bias + ReLU /
+    softmax / arg-max) must equal the reference order (dense conv2d_transpose x8, then 1x1 at full resolution)."""
+    net, data, meta, ext, out = net_and_out
+    f = lambda k: out[k].float().permute(0, 3, 1, 2)
+    score, label, prob, vertex = R.heads_from_scores(net.params, f("score_conv4"), f("score_conv5"), f("score_conv4_vertex"),
+                                                     f("score_conv5_vertex"))
+    got_v = out["vertex_pred"].permute(0, 3, 1, 2)
+    assert torch.allclose(got_v, vertex, rtol=1e-4, atol=1e-4 * vertex.abs().max().item())
+    got_p = out["prob_normalized"].permute(0, 3, 1, 2)
+    assert torch.allclose(got_p, prob, atol=1e-5)
+    top2 = torch.topk(score, 2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-5 * top2[:, 0].abs().clamp(min=1.0)   # arg-max is exact away from ties
+    assert decided.float().mean() > 0.5
+    assert torch.equal(out["label_2d"][decided], label[decided])
+    ties = ~decided
+    if ties.any():  # exact ties (e.g. all-zero after ReLU): lowest index, like tf.argmax
+        zero = ties & (top2[:, 0] == top2[:, 1])
+        assert (out["label_2d"][zero] <= label[zero]).all()
+
+
+def test_end_to_end_label_flip_rate(net_and_out):
+    net, data, meta, ext, out = net_and_out
+    x = (data.float() - torch.tensor([102.9801, 115.9465, 122.7717], device=data.device)).permute(0, 3, 1, 2)
+    feats = R.trunk(net.params, x)
+    score, label, prob, vertex = R.heads(net.params, feats["conv4_3"], feats["conv5_3"], 6)
+    got_v = out["vertex_pred"].permute(0, 3, 1, 2)
+    assert rel_l2(got_v, vertex) < 2e-2
+    top2 = torch.topk(score, 2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1]) / top2[:, 0].abs().clamp(min=1e-6)
+    safe = margin > 0.05            # BF16 trunk: labels are compared where the fp32 logit margin exceeds 5 %
+    flips = (out["label_2d"][safe] != label[safe]).float().mean().item()
+    print("label flip rate outside the 5% margin:", flips, "pixels compared:", int(safe.sum()))
+    assert flips < 1e-3
+
+
+def test_hough_roi_pose_head_composition(net_and_out):
+    """rois / poses_init from the pipeline == oracle Hough on the pipeline's own label / vertex maps; poses_tanh ==
+    fp32 torch pose head on the pipeline's conv features and rois (bf16 GEMMs: abs 1e-2 on tanh outputs)."""
+    net, data, meta, ext, out = net_and_out
+    want = oracle.hough_voting_gpu(to_np(out["label_2d"]), to_np(out["vertex_pred"]), to_np(ext), to_np(meta), None, 0, -1.0,
+                                   0.02, 10)
+    assert out["rois"].shape == want[0].shape
+    np.testing.assert_array_equal(to_np(out["rois"])[:, [0, 1, 6]], want[0][:, [0, 1, 6]])
+    np.testing.assert_allclose(to_np(out["rois"])[:, 2:6], want[0][:, 2:6], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(to_np(out["poses_init"]), want[1], rtol=1e-4, atol=1e-4)
+    rois = to_np(out["rois"])
+    p5, _ = oracle.roi_pool(to_np(out["conv5_3"].float()), rois, 7, 7, 1.0 / 16.0)
+    p4, _ = oracle.roi_pool(to_np(out["conv4_3"].float()), rois, 7, 7, 1.0 / 8.0)
+    x = torch.from_numpy(p5 + p4).reshape(rois.shape[0], -1).to(data.device)
+    P = net.params
+    x = torch.relu(x @ P["fc6/weights"] + P["fc6/biases"])
+    x = torch.relu(x @ P["fc7/weights"] + P["fc7/biases"])
+    x = torch.tanh(x @ P["fc8/weights"] + P["fc8/biases"])
+    assert torch.allclose(out["poses_tanh"], x, atol=2e-2)
