@@ -84,6 +84,10 @@ int pcnn_hough_vote_bwd(float* grad_label, float* grad_vertex, int B, int H, int
 int pcnn_roi_pool_fwd(const float* bottom, const float* rois, int num_rois, int channel_rois, int batch,
                       int height, int width, int channels, int pooled_height, int pooled_width,
                       float spatial_scale, int pool_channel, float* top, int32_t* argmax, void* stream);
+/* same forward reading bf16 NHWC features (the tensor-core trunk's activation format); channels % 8 == 0 */
+int pcnn_roi_pool_fwd_bf16(const void* bottom_bf16, const float* rois, int num_rois, int channel_rois, int batch,
+                           int height, int width, int channels, int pooled_height, int pooled_width,
+                           float spatial_scale, float* top, int32_t* argmax, void* stream);
 int pcnn_roi_pool_bwd(const float* top_diff, const int32_t* argmax, const float* rois, int batch, int num_rois,
                       int channel_rois, int height, int width, int channels, int pooled_height,
                       int pooled_width, float spatial_scale, int pool_channel, float* bottom_diff,

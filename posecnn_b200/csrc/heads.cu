@@ -29,6 +29,9 @@ namespace pcnn {
 // make_deconv_filter (network.py:141-157): f = ceil(k/2), c = (2f - 1 - f%2) / (2f), W[x] = 1 - |x/f - c|
 __host__ __device__ inline float deconv_w(int x, int k)
 {
+    // k = 16: f = 8, c = 15/16; k = 4: f = 2, c = 3/4 (exact in binary floating point)
+    if (k == 16) return 1.f - fabsf((float)x * 0.125f - 0.9375f);
+    if (k == 4) return 1.f - fabsf((float)x * 0.5f - 0.75f);
     int f = (k + 1) / 2;
     float c = (2.f * f - 1.f - (float)(f % 2)) / (2.f * f);
     return 1.f - fabsf((float)x / (float)f - c);
@@ -37,7 +40,7 @@ __host__ __device__ inline float deconv_w(int x, int k)
 // ---------------------------------------------------------------------------------------------
 // k_lowres_heads: 8 low-resolution pixels per CTA
 // ---------------------------------------------------------------------------------------------
-constexpr int kLrPix = 8;
+constexpr int kLrPix = 16;
 
 __global__ void __launch_bounds__(256)
 k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_bfloat16* __restrict__ s5 /*[B,h/2,w/2,Cs]*/,
@@ -52,23 +55,23 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
     float* sx = sm + Cs * C + Cv * 3 * C;  // [kLrPix][Ct]
     for (int i = threadIdx.x; i < Cs * C; i += blockDim.x) sW[i] = Ws[i];
     for (int i = threadIdx.x; i < Cv * 3 * C; i += blockDim.x) sW[Cs * C + i] = Wv[i];
-    const size_t npix = (size_t)B * h * w;
+    const int npix = B * h * w;
     const int h5 = h / 2, w5 = w / 2;
-    for (size_t p0 = (size_t)blockIdx.x * kLrPix; p0 < npix; p0 += (size_t)gridDim.x * kLrPix) {
+    for (int p0 = blockIdx.x * kLrPix; p0 < npix; p0 += gridDim.x * kLrPix) {
         __syncthreads();
         // add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
         for (int i = threadIdx.x; i < kLrPix * Ct; i += blockDim.x) {
             const int pi = i / Ct, ch = i % Ct;
-            const size_t p = p0 + pi;
+            const int p = p0 + pi;
             float val = 0.f;
             if (p < npix) {
-                const int x = (int)(p % w), y = (int)((p / w) % h);
-                const size_t n = p / ((size_t)w * h);
+                const int x = p % w, y = (p / w) % h;
+                const int n = p / (w * h);
                 const bool vert = ch >= Cs;
                 const int cc = vert ? ch - Cs : ch, Cn = vert ? Cv : Cs;
                 const __nv_bfloat16* a = vert ? v4 : s4;
                 const __nv_bfloat16* b5 = vert ? v5 : s5;
-                val = __bfloat162float(a[p * Cn + cc]);
+                val = __bfloat162float(a[(size_t)p * Cn + cc]);
                 // out[o] += in[i] * W[o - 2 i + 1], 0 <= o - 2i + 1 <= 3
                 const int iy0 = ((y + 1) >> 1) - 1, ix0 = ((x + 1) >> 1) - 1;
                 float up = 0.f;
@@ -80,7 +83,7 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
                     for (int dx = 0; dx < 2; dx++) {
                         const int ix = ix0 + dx, kx = x - 2 * ix + 1;
                         if (ix < 0 || ix >= w5 || kx < 0 || kx > 3) continue;
-                        up += deconv_w(ky, 4) * deconv_w(kx, 4) * __bfloat162float(b5[((n * h5 + iy) * w5 + ix) * Cn + cc]);
+                        up += deconv_w(ky, 4) * deconv_w(kx, 4) * __bfloat162float(b5[((size_t)(n * h5 + iy) * w5 + ix) * Cn + cc]);
                     }
                 }
                 val += up;
@@ -90,7 +93,7 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
         __syncthreads();
         for (int i = threadIdx.x; i < kLrPix * No; i += blockDim.x) {
             const int pi = i / No, o = i % No;
-            const size_t p = p0 + pi;
+            const int p = p0 + pi;
             if (p >= npix) continue;
             float acc = 0.f;
             if (o < C) {
@@ -101,79 +104,81 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
                 const float* wv = sW + Cs * C + (o - C);
                 for (int k = 0; k < Cv; k++) acc = fmaf(x[k], wv[k * 3 * C], acc);
             }
-            out[p * No + o] = acc;
+            out[(size_t)p * No + o] = acc;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_up8_heads: one warp per output pixel (lanes over channels)
+// k_up8_heads: one CTA per output row (y, image).  The two contributing low-resolution rows are
+// combined vertically into shared memory once; every output value is then a 2-tap horizontal blend.
+// Class scores of the row are kept in shared memory for the per-pixel arg-max / softmax.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/,
-            const float* __restrict__ bias_v /*[3C]*/, int B, int h, int w, int C, int* __restrict__ label /*[B,8h,8w]*/,
+            const float* __restrict__ bias_v /*[3C]*/, int h, int w, int C, int* __restrict__ label /*[B,8h,8w]*/,
             float* __restrict__ vertex /*[B,8h,8w,3C]*/, float* __restrict__ prob /*[B,8h,8w,C] or null*/,
             float* __restrict__ score_out /*[B,8h,8w,C] or null*/)
 {
-    const int lane = threadIdx.x & 31;
-    const int H = 8 * h, W = 8 * w, No = 4 * C;
-    const size_t npix = (size_t)B * H * W;
-    const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const int rounds = (No + 31) / 32;
-    for (size_t p = warp0; p < npix; p += nwarps) {
-        const int x = (int)(p % W), y = (int)((p / W) % H);
-        const size_t n = p / ((size_t)W * H);
-        // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
-        const int my = y >> 3, ty = y & 7, mx = x >> 3, tx = x & 7;
-        const int iy0 = ty < 4 ? my - 1 : my, ix0 = tx < 4 ? mx - 1 : mx;
-        float wy[2], wx[2];
-        int iy[2], ix[2];
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            iy[d] = iy0 + d; ix[d] = ix0 + d;
-            wy[d] = (iy[d] >= 0 && iy[d] < h) ? deconv_w(y - 8 * iy[d] + 4, 16) : 0.f;
-            wx[d] = (ix[d] >= 0 && ix[d] < w) ? deconv_w(x - 8 * ix[d] + 4, 16) : 0.f;
-            iy[d] = min(max(iy[d], 0), h - 1); ix[d] = min(max(ix[d], 0), w - 1);
-        }
-        const float* base = lr + n * (size_t)h * w * No;
-        const float* p00 = base + ((size_t)iy[0] * w + ix[0]) * No;
-        const float* p01 = base + ((size_t)iy[0] * w + ix[1]) * No;
-        const float* p10 = base + ((size_t)iy[1] * w + ix[0]) * No;
-        const float* p11 = base + ((size_t)iy[1] * w + ix[1]) * No;
-        const float w00 = wy[0] * wx[0], w01 = wy[0] * wx[1], w10 = wy[1] * wx[0], w11 = wy[1] * wx[1];
-        float sc = -FLT_MAX;  // this lane's class score (lanes < C), first round only when C <= 32
-        for (int r = 0; r < rounds; r++) {
-            const int ch = r * 32 + lane;
-            if (ch >= No) break;
-            // same accumulation order as a (ky, kx) loop of the transposed convolution
-            float v = w00 * __ldg(p00 + ch);
-            v = fmaf(w01, __ldg(p01 + ch), v);
-            v = fmaf(w10, __ldg(p10 + ch), v);
-            v = fmaf(w11, __ldg(p11 + ch), v);
-            if (ch < C) {
-                v = fmaxf(v + __ldg(bias_s + ch), 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
-                sc = v;
-                if (score_out) score_out[p * C + ch] = v;
+    // C even: every channel pair is one 8-byte vector (vertex rows are 3C floats = 8-byte aligned)
+    extern __shared__ float smem_f[];
+    const int No = 4 * C, W = 8 * w, H = 8 * h, N2 = No / 2, C2 = C / 2;
+    float2* rowi = reinterpret_cast<float2*>(smem_f);   // [w][N2] vertically interpolated low-res row
+    float2* sbias = rowi + w * N2;                      // [N2]
+    const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
+    const int my = y >> 3, ty = y & 7;
+    const int iy0 = ty < 4 ? my - 1 : my, iy1 = iy0 + 1;
+    const float wy0 = (iy0 >= 0 && iy0 < h) ? deconv_w(y - 8 * iy0 + 4, 16) : 0.f;
+    const float wy1 = (iy1 >= 0 && iy1 < h) ? deconv_w(y - 8 * iy1 + 4, 16) : 0.f;
+    const float2* r0 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy0, 0), h - 1)) * w * No);
+    const float2* r1 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy1, 0), h - 1)) * w * No);
+    for (int i = t; i < w * N2; i += 256) {
+        const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
+        rowi[i] = make_float2(fmaf(wy1, b.x, wy0 * a.x), fmaf(wy1, b.y, wy0 * a.y));
+    }
+    for (int i = t; i < N2; i += 256)
+        sbias[i] = i < C2 ? make_float2(bias_s[2 * i], bias_s[2 * i + 1]) : make_float2(bias_v[2 * i - C], bias_v[2 * i + 1 - C]);
+    __syncthreads();
+    const size_t rowbase = ((size_t)n * H + y) * W;
+    // one warp per output pixel, lanes over channel pairs
+    for (int x = warp; x < W; x += 8) {
+        const int mx = x >> 3, tx = x & 7;
+        const int ix0 = tx < 4 ? mx - 1 : mx, ix1 = ix0 + 1;
+        const float wx0 = (ix0 >= 0) ? deconv_w(tx < 4 ? tx + 12 : tx + 4, 16) : 0.f;
+        const float wx1 = (ix1 < w) ? deconv_w(tx < 4 ? tx + 4 : tx - 4, 16) : 0.f;
+        const float2* a = rowi + max(ix0, 0) * N2;
+        const float2* b = rowi + min(ix1, w - 1) * N2;
+        float s0 = -FLT_MAX, s1 = -FLT_MAX;  // this lane's two class scores (lanes < C/2)
+        for (int c2 = lane; c2 < N2; c2 += 32) {
+            const float2 va = a[c2], vb = b[c2], bb = sbias[c2];
+            float v0 = fmaf(wx1, vb.x, wx0 * va.x) + bb.x;
+            float v1 = fmaf(wx1, vb.y, wx0 * va.y) + bb.y;
+            if (c2 < C2) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
+                s0 = v0; s1 = v1;
+                if (score_out) *reinterpret_cast<float2*>(score_out + (rowbase + x) * C + 2 * c2) = make_float2(v0, v1);
             } else {
-                vertex[p * 3 * C + (ch - C)] = v + __ldg(bias_v + ch - C);
+                *reinterpret_cast<float2*>(vertex + (rowbase + x) * 3 * C + 2 * (c2 - C2)) = make_float2(v0, v1);
             }
         }
-        // arg-max over classes, lowest index wins ties (tf.argmax); softmax for prob_normalized
-        float best = sc;
-        int bi = lane < C ? lane : 0x7fffffff;
+        // arg-max over classes, lowest index wins ties (tf.argmax)
+        float best = s0;
+        int bi = lane < C2 ? 2 * lane : 0x7fffffff;
+        if (s1 > best) { best = s1; bi = 2 * lane + 1; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
-        if (lane == 0) label[p] = bi;
-        if (prob) {
-            float e = lane < C ? expf(sc - best) : 0.f;  // softmax_high_dimension, network.py:474-488
-            float s = e;
+        if (lane == 0) label[rowbase + x] = bi;
+        if (prob) {  // softmax_high_dimension, network.py:474-488
+            const float e0 = lane < C2 ? expf(s0 - best) : 0.f, e1 = lane < C2 ? expf(s1 - best) : 0.f;
+            float sum = e0 + e1;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane < C) prob[p * C + lane] = e / s;
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane < C2) *reinterpret_cast<float2*>(prob + (rowbase + x) * C + 2 * lane) = make_float2(e0 / sum, e1 / sum);
         }
     }
 }
@@ -219,6 +224,7 @@ extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const v
     PCNN_REQUIRE(smem <= 200 * 1024, "lowres_heads: weights do not fit shared memory");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lowres_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    PCNN_REQUIRE((long long)B * h * w < 0x7fffffffLL, "lowres_heads: too many pixels");
     size_t npix = (size_t)B * h * w;
     int blocks = (int)std::min<size_t>((npix + kLrPix - 1) / kLrPix, (size_t)kNumSMs * 4);
     k_lowres_heads<<<blocks, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)score4, (const __nv_bfloat16*)score5,
@@ -231,10 +237,15 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
                               int32_t* label, float* vertex, float* prob, float* score, void* stream)
 {
     PCNN_REQUIRE(lowres && bias_score && bias_vertex && label && vertex, "up8_heads: NULL tensor pointer");
-    PCNN_REQUIRE(C >= 1 && C <= 32, "up8_heads: 1 <= num_classes <= 32 (got %d)", C);
-    size_t npix = (size_t)B * h * w * 64;
-    int blocks = (int)std::min<size_t>((npix + 7) / 8, (size_t)kNumSMs * 32);
-    k_up8_heads<<<blocks, 256, 0, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, B, h, w, C, label, vertex, prob, score);
+    PCNN_REQUIRE(C >= 1 && B >= 1 && h >= 1 && w >= 1, "up8_heads: bad shape");
+    PCNN_REQUIRE(8 * h <= 65535 * 1 && B <= 65535, "up8_heads: image too tall for the launch grid");
+    PCNN_REQUIRE(C % 2 == 0 && C <= 64, "up8_heads: num_classes must be even and <= 64 (got %d)", C);
+    size_t smem = sizeof(float) * ((size_t)w * 4 * C + 4 * C);
+    PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: row does not fit shared memory (w = %d, C = %d)", w, C);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_up8_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    dim3 grid(8 * h, B);
+    k_up8_heads<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, label, vertex, prob, score);
     return check_launch("up8_heads");
 }
 

@@ -10,6 +10,7 @@
 //   Hardlabel        hard_label_layer/hard_label_op_gpu.cu.cc:16-29, 54-63
 //   Project          projecting_layer/projecting_op_gpu.cu.cc:16-73, 101-169
 //   Backproject      backprojecting_layer/backprojecting_op_gpu.cu.cc:16-126, 158-217
+#include <cuda_bf16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -97,6 +98,51 @@ k_roi_pool_fwd(const float* __restrict__ bottom, const float* __restrict__ rois,
             top[o] = mv[0];
             argmax[o] = mi[0];
         }
+    }
+}
+
+// same forward on bf16 NHWC features (the tensor-core trunk keeps activations in bf16): 8 channels per thread,
+// fp32 outputs; comparisons are done on the bf16 values converted to fp32 (exact), so argmax is well defined
+__global__ void __launch_bounds__(256)
+k_roi_pool_fwd_bf16(const __nv_bfloat16* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois,
+                    int batch, int height, int width, int channels, int ph_n, int pw_n, float scale, float* __restrict__ top,
+                    int* __restrict__ argmax)
+{
+    const int cg = channels / 8;
+    const size_t total = (size_t)num_rois * ph_n * pw_n * cg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(idx % cg);
+        size_t r1 = idx / cg;
+        int pw = (int)(r1 % pw_n);
+        r1 /= pw_n;
+        int ph = (int)(r1 % ph_n);
+        int n = (int)(r1 / ph_n);
+        RoiBin rb = roi_bin(rois + (size_t)n * channel_rois, ph, pw, ph_n, pw_n, scale, height, width);
+        bool empty = (rb.he <= rb.hs) || (rb.we <= rb.ws) || rb.b < 0 || rb.b >= batch;
+        float mv[8];
+        int mi[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { mv[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
+        if (!empty) {
+            const __nv_bfloat16* img = bottom + (size_t)rb.b * height * width * channels;
+            for (int h = rb.hs; h < rb.he; h++)
+                for (int w = rb.ws; w < rb.we; w++) {
+                    int bi = (h * width + w) * channels + g * 8;
+                    uint4 q = __ldg(reinterpret_cast<const uint4*>(img + bi));
+                    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float2 f = __bfloat1622float2(q2[k]);
+                        if (f.x > mv[2 * k]) { mv[2 * k] = f.x; mi[2 * k] = bi + 2 * k; }
+                        if (f.y > mv[2 * k + 1]) { mv[2 * k + 1] = f.y; mi[2 * k + 1] = bi + 2 * k + 1; }
+                    }
+                }
+        }
+        size_t o = ((size_t)(n * ph_n + ph) * pw_n + pw) * channels + g * 8;
+        *reinterpret_cast<float4*>(top + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        *reinterpret_cast<float4*>(top + o + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+        *reinterpret_cast<int4*>(argmax + o) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+        *reinterpret_cast<int4*>(argmax + o + 4) = make_int4(mi[4], mi[5], mi[6], mi[7]);
     }
 }
 
@@ -545,4 +591,19 @@ extern "C" int pcnn_project_bwd(const float* top_diff, const float* depth, const
     PCNN_REQUIRE(num_meta >= 48 && grid_size >= 1, "project_grad: bad meta/grid");
     return launch_average(top_diff, depth, meta, nullptr, B, H, W, Cf, num_meta, grid_size, kernel_size, threshold,
                           bottom_diff, nullptr, (cudaStream_t)stream);
+}
+
+// RoiPool forward on bf16 NHWC features (channels % 8 == 0), fp32 top + int32 argmax
+extern "C" int pcnn_roi_pool_fwd_bf16(const void* bottom_bf16, const float* rois, int num_rois, int channel_rois, int batch,
+                                      int height, int width, int channels, int pooled_height, int pooled_width,
+                                      float spatial_scale, float* top, int32_t* argmax, void* stream)
+{
+    PCNN_REQUIRE(bottom_bf16 && rois && top && argmax, "roi_pool_bf16: NULL tensor pointer");
+    PCNN_REQUIRE(channel_rois >= 6 && channels % 8 == 0, "roi_pool_bf16: needs >= 6 roi columns and channels %% 8 == 0");
+    if (num_rois == 0 || pooled_height == 0 || pooled_width == 0) return PCNN_OK;
+    size_t total = (size_t)num_rois * pooled_height * pooled_width * (channels / 8);
+    k_roi_pool_fwd_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)bottom_bf16, rois, num_rois, channel_rois, batch, height, width, channels, pooled_height,
+        pooled_width, spatial_scale, top, argmax);
+    return check_launch("roi_pool_fwd_bf16");
 }

@@ -89,6 +89,26 @@ class vgg16_convs:
         self.prepare()
         return self
 
+    def calibrate_background(self, data, meta_data, extents, background_fraction=0.75):
+        """Benchmark-harness helper: a randomly initialised net labels (almost) every pixel as foreground, which is
+        not what the Hough layer sees in use.  Shift `score/biases[0]` so that about `background_fraction` of the
+        pixels of this batch are labelled background (YCB-like fill).  Declared in bench.py's config."""
+        L = self.forward(data, meta_data, extents, want_prob=False, sync_rois=False)
+        C = self.num_classes
+        B, H, W, _ = data.shape
+        score = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device)
+        lab = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
+        vert = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
+        # re-run the streaming head with the raw scores exposed
+        lowres = self._last_lowres
+        check(lib().pcnn_up8_heads(ptr(lowres), ptr(self.params["score/biases"]), ptr(self.params["vertex_pred/biases"]), B,
+                                   H // 8, W // 8, C, ptr(lab), ptr(vert), ptr(None), ptr(score), stream()))
+        gap = (score[..., 1:].max(dim=-1).values - score[..., 0]).flatten()
+        sub = gap[:: max(1, gap.numel() // 2000000)]
+        shift = float(torch.kthvalue(sub, max(1, int(background_fraction * sub.numel()))).values)
+        self.params["score/biases"][0] += shift + 1e-3
+        return shift
+
     def load(self, data_dict: dict):
         """TF-name dictionary {layer: {'weights': ..., 'biases': ...}} (VGG16 .npy, network.py:71-107) or flat
         {'layer/weights': ...}."""
@@ -165,6 +185,7 @@ class vgg16_convs:
         lowres = torch.empty((B, h, w, 4 * C), dtype=torch.float32, device=data.device)
         check(lib().pcnn_lowres_heads(ptr(s4), ptr(s5), ptr(v4), ptr(v5), ptr(T["score/w"]), ptr(T["vertex_pred/w"]), B, h, w,
                                       self.num_units, 128, C, ptr(lowres), stream()))
+        self._last_lowres = lowres
         label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
         vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
         prob = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_prob else None
@@ -183,8 +204,8 @@ class vgg16_convs:
         L["rois_capacity"], L["num_rois"] = rois, num_rois
         L["poses_init"], L["poses_target"], L["poses_weight"] = pose[:cap_rows], target[:cap_rows], weight[:cap_rows]
         if self.pose_reg:
-            p5, _ = roi_pooling_op.roi_pool(c5.float(), rois, 7, 7, 1.0 / 16.0, 0)
-            p4, _ = roi_pooling_op.roi_pool(c4.float(), rois, 7, 7, 1.0 / 8.0, 0)
+            p5, _ = roi_pooling_op.roi_pool(c5, rois, 7, 7, 1.0 / 16.0, 0)
+            p4, _ = roi_pooling_op.roi_pool(c4, rois, 7, 7, 1.0 / 8.0, 0)
             x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                     # pool_score, flatten (h, w, c)
             x = torch.relu(torch.nn.functional.linear(x, T["fc6/weights"], P["fc6/biases"].to(torch.bfloat16)))
             x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], P["fc7/biases"].to(torch.bfloat16)))

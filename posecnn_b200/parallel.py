@@ -1,0 +1,41 @@
+"""Image-sharded multi-GPU inference: one process per GPU, every rank runs the whole
+network on its own contiguous shard of images; the only exchange is one NCCL all-gather of the fixed-size
+per-rank hypothesis records (ROI rows, initial poses, regressed quaternions, row count) over NVLink.
+
+The reference has no distributed code at all (SURVEY finding 9); this is new design.  Each rank's shard is
+treated as one reference batch: the MAX_ROI / batch_size cap (hough_voting_gpu_op.cu.cc:733) is applied to
+the rank-local batch, and batch indices in the gathered ROI rows are made global (rank * local_batch + b).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def record_width(num_classes: int) -> int:
+    return 7 + 7 + 4 * num_classes + 1  # roi row, initial pose, tanh quaternions, valid flag
+
+
+def pack_records(layers: dict, num_classes: int, rank: int, local_batch: int) -> torch.Tensor:
+    """[cap_rows, 7 + 7 + 4C + 1] f32; rows >= num_rois carry valid = 0 (no host sync needed)."""
+    rois = layers["rois_capacity"]
+    n = rois.shape[0]
+    rec = torch.zeros((n, record_width(num_classes)), dtype=torch.float32, device=rois.device)
+    rec[:, 0:7] = rois
+    rec[:, 0] += float(rank * local_batch)
+    rec[:, 7:14] = layers["poses_init"][:n]
+    if "poses_tanh" in layers:
+        rec[:, 14:14 + 4 * num_classes] = layers["poses_tanh"][:n]
+    valid = torch.arange(n, device=rois.device) < layers["num_rois"].to(torch.int64)
+    rec[:, -1] = valid.float()
+    rec[:, 0] *= rec[:, -1]
+    return rec
+
+
+def all_gather_records(rec: torch.Tensor, world: int) -> torch.Tensor:
+    """[world * cap_rows, width]; latency-bound (tens of KB), one ncclAllGather."""
+    if world == 1:
+        return rec
+    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous())
+    return out

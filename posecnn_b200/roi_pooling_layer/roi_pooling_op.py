@@ -15,6 +15,17 @@ except ImportError:
 
 
 def roi_pool(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale, pool_channel=0, name=None):
+    if isinstance(bottom_data, torch.Tensor) and bottom_data.dtype == torch.bfloat16 and not pool_channel:
+        # activation format of the tensor-core trunk; same semantics, fp32 outputs
+        data = require_cuda("bottom_data", bottom_data, torch.bfloat16, 4)
+        rois = require_cuda("bottom_rois", bottom_rois, torch.float32, 2)
+        B, H, W, C = data.shape
+        N, cr = rois.shape
+        top = torch.empty((N, pooled_height, pooled_width, C), dtype=torch.float32, device=data.device)
+        argmax = torch.empty((N, pooled_height, pooled_width, C), dtype=torch.int32, device=data.device)
+        check(lib().pcnn_roi_pool_fwd_bf16(ptr(data), ptr(rois), N, cr, B, H, W, C, int(pooled_height), int(pooled_width),
+                                           f32(spatial_scale), ptr(top), ptr(argmax), stream()))
+        return top, argmax
     data = require_cuda("bottom_data", bottom_data, torch.float32, 4)   # roi_pooling_op.cc:297-298
     rois = require_cuda("bottom_rois", bottom_rois, torch.float32, 2)   # roi_pooling_op.cc:301-302
     B, H, W, C = data.shape
