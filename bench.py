@@ -217,8 +217,11 @@ def run_full(args, rank, world, local):
     bg_shift = net.calibrate_background(d_img, meta, ext, 0.75)  # declared harness choice, see config
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    from posecnn_b200.networks.vgg16_convs import GraphedForward
+    fwd = None if args.no_graph else GraphedForward(net, d_img, meta, ext)
+
     def step(img):
-        L = net.forward(img, meta, ext, sync_rois=False)
+        L = fwd(img) if fwd is not None else net.forward(img, meta, ext, sync_rois=False)
         rec = parallel.pack_records(L, C, rank, B)
         return parallel.all_gather_records(rec, world), L
 
@@ -297,7 +300,7 @@ def run_full(args, rank, world, local):
         config=dict(workload="configs[2]: full VGG16+Hough+ROI inference, random-init (Kaiming, seed 0) weights, batch %d, "
                              "640x480 uint8 BGR" % B, global_batch=B * world, per_gpu_batch=B,
                     parallelism="image-sharded x%d, NCCL all-gather of pose-hypothesis records" % world,
-                    l2="flushed between timed iterations (256 MB write)", rois_last_step=nrois,
+                    l2="flushed between timed iterations (256 MB write)", rois_last_step=nrois, cuda_graph=not args.no_graph,
                     foreground_fraction=nlabels / float(B * H * W),
                     background_calibration="score/biases[0] += %.4g so that ~75%% of pixels are background (YCB-like fill); "
                                            "un-calibrated random init labels ~100%% of pixels foreground" % bg_shift),
@@ -353,6 +356,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

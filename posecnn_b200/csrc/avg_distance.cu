@@ -29,7 +29,7 @@ k_average_distance(const float* __restrict__ pred, const float* __restrict__ tar
                    float* __restrict__ loss, float* __restrict__ bottom_diff, float* __restrict__ roi_loss,
                    unsigned* __restrict__ done_ctr)
 {
-    extern __shared__ float sh[];       // [3*P] gt-rotated points (symmetric classes only)
+    extern __shared__ float4 sh4[];     // [P] gt-rotated points (symmetric classes only), one 16-byte load each
     __shared__ float s_red[5][kAdThreads];
     __shared__ int s_cls;
     __shared__ bool s_last;
@@ -58,9 +58,8 @@ k_average_distance(const float* __restrict__ pred, const float* __restrict__ tar
         if (sym) {
             for (int i = t; i < P; i += kAdThreads) {
                 float q0 = pts[3 * i], q1 = pts[3 * i + 1], q2 = pts[3 * i + 2];
-                sh[3 * i + 0] = Rg[0] * q0 + Rg[1] * q1 + Rg[2] * q2;
-                sh[3 * i + 1] = Rg[3] * q0 + Rg[4] * q1 + Rg[5] * q2;
-                sh[3 * i + 2] = Rg[6] * q0 + Rg[7] * q1 + Rg[8] * q2;
+                sh4[i] = make_float4(Rg[0] * q0 + Rg[1] * q1 + Rg[2] * q2, Rg[3] * q0 + Rg[4] * q1 + Rg[5] * q2,
+                                     Rg[6] * q0 + Rg[7] * q1 + Rg[8] * q2, 0.f);
             }
             __syncthreads();
         }
@@ -74,12 +73,15 @@ k_average_distance(const float* __restrict__ pred, const float* __restrict__ tar
             if (sym) {
                 float dmin = FLT_MAX;
                 int jmin = 0;
+#pragma unroll 8
                 for (int i = 0; i < P; i++) {  // first minimum wins, .cu.cc:152-169
-                    float ex = x1 - sh[3 * i], ey = y1 - sh[3 * i + 1], ez = z1 - sh[3 * i + 2];
+                    const float4 g4 = sh4[i];
+                    float ex = x1 - g4.x, ey = y1 - g4.y, ez = z1 - g4.z;
                     float dd = ex * ex + ey * ey + ez * ez;
                     if (dd < dmin) { dmin = dd; jmin = i; }
                 }
-                x2 = sh[3 * jmin]; y2 = sh[3 * jmin + 1]; z2 = sh[3 * jmin + 2];
+                const float4 gm = sh4[jmin];
+                x2 = gm.x; y2 = gm.y; z2 = gm.z;
             } else {
                 x2 = Rg[0] * q0 + Rg[1] * q1 + Rg[2] * q2;
                 y2 = Rg[3] * q0 + Rg[4] * q1 + Rg[5] * q2;
@@ -172,7 +174,7 @@ extern "C" int pcnn_average_distance_fwd(const float* prediction, const float* t
     cudaMemsetAsync(workspace, 0, 256, st);  // completion counter
     cudaMemsetAsync(loss, 0, sizeof(float), st);
     if (N == 0) return PCNN_OK;
-    size_t smem = sizeof(float) * 3 * (size_t)P;
+    size_t smem = sizeof(float4) * (size_t)P;
     PCNN_REQUIRE(smem <= 200 * 1024, "average_distance: P = %d model points exceed the shared-memory staging", P);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_average_distance, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }

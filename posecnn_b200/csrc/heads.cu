@@ -124,8 +124,8 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     extern __shared__ float smem_f[];
     const int No = 4 * C, W = 8 * w, H = 8 * h, N2 = No / 2, C2 = C / 2;
     float2* rowi = reinterpret_cast<float2*>(smem_f);   // [w][N2] vertically interpolated low-res row
-    float2* sbias = rowi + w * N2;                      // [N2]
-    const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float* sc = smem_f + (size_t)w * No;                // [W][C]  class scores of this output row
+    const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
     // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
     const int my = y >> 3, ty = y & 7;
     const int iy0 = ty < 4 ? my - 1 : my, iy1 = iy0 + 1;
@@ -137,48 +137,55 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
         const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
         rowi[i] = make_float2(fmaf(wy1, b.x, wy0 * a.x), fmaf(wy1, b.y, wy0 * a.y));
     }
-    for (int i = t; i < N2; i += 256)
-        sbias[i] = i < C2 ? make_float2(bias_s[2 * i], bias_s[2 * i + 1]) : make_float2(bias_v[2 * i - C], bias_v[2 * i + 1 - C]);
     __syncthreads();
     const size_t rowbase = ((size_t)n * H + y) * W;
-    // one warp per output pixel, lanes over channel pairs
-    for (int x = warp; x < W; x += 8) {
-        const int mx = x >> 3, tx = x & 7;
-        const int ix0 = tx < 4 ? mx - 1 : mx, ix1 = ix0 + 1;
-        const float wx0 = (ix0 >= 0) ? deconv_w(tx < 4 ? tx + 12 : tx + 4, 16) : 0.f;
-        const float wx1 = (ix1 < w) ? deconv_w(tx < 4 ? tx + 4 : tx - 4, 16) : 0.f;
-        const float2* a = rowi + max(ix0, 0) * N2;
-        const float2* b = rowi + min(ix1, w - 1) * N2;
-        float s0 = -FLT_MAX, s1 = -FLT_MAX;  // this lane's two class scores (lanes < C/2)
-        for (int c2 = lane; c2 < N2; c2 += 32) {
-            const float2 va = a[c2], vb = b[c2], bb = sbias[c2];
-            float v0 = fmaf(wx1, vb.x, wx0 * va.x) + bb.x;
-            float v1 = fmaf(wx1, vb.y, wx0 * va.y) + bb.y;
-            if (c2 < C2) {
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
-                s0 = v0; s1 = v1;
-                if (score_out) *reinterpret_cast<float2*>(score_out + (rowbase + x) * C + 2 * c2) = make_float2(v0, v1);
-            } else {
-                *reinterpret_cast<float2*>(vertex + (rowbase + x) * 3 * C + 2 * (c2 - C2)) = make_float2(v0, v1);
+    // thread = (cell phase g, channel pair c2): a fixed channel pair, strided over the low-resolution cells of the
+    // row; the 8 output pixels of a cell blend the same three source values with compile-time weights.  Consecutive
+    // lanes hold consecutive channel pairs, so the vertex stores of a pixel are contiguous.
+    const int groups = 256 / N2;
+    const int g = t / N2, c2 = t - g * N2;
+    if (g < groups) {
+        const float2 bb = c2 < C2 ? make_float2(bias_s[2 * c2], bias_s[2 * c2 + 1])
+                                  : make_float2(bias_v[2 * c2 - C], bias_v[2 * c2 + 1 - C]);
+        const bool is_score = c2 < C2;
+        float* vbase = vertex + rowbase * 3 * C + 2 * (c2 - C2);
+        for (int mx = g; mx < w; mx += groups) {
+            const float2 zero = make_float2(0.f, 0.f);
+            const float2 vl = mx > 0 ? rowi[(mx - 1) * N2 + c2] : zero;
+            const float2 vc = rowi[mx * N2 + c2];
+            const float2 vr = mx + 1 < w ? rowi[(mx + 1) * N2 + c2] : zero;
+#pragma unroll
+            for (int tx = 0; tx < 8; tx++) {
+                // x = 8 mx + tx: sources (mx-1, mx) with taps (tx+12, tx+4) for tx < 4, (mx, mx+1) with (tx+4, tx-4) otherwise
+                const float wa = deconv_w(tx < 4 ? tx + 12 : tx + 4, 16), wb = deconv_w(tx < 4 ? tx + 4 : tx - 4, 16);
+                const float2 a = tx < 4 ? vl : vc, b = tx < 4 ? vc : vr;
+                float v0 = fmaf(wb, b.x, wa * a.x) + bb.x;
+                float v1 = fmaf(wb, b.y, wa * a.y) + bb.y;
+                const int x = 8 * mx + tx;
+                if (is_score) {
+                    v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
+                    *reinterpret_cast<float2*>(sc + x * C + 2 * c2) = make_float2(v0, v1);
+                    if (score_out) *reinterpret_cast<float2*>(score_out + (rowbase + x) * C + 2 * c2) = make_float2(v0, v1);
+                } else {
+                    *reinterpret_cast<float2*>(vbase + (size_t)x * 3 * C) = make_float2(v0, v1);
+                }
             }
         }
-        // arg-max over classes, lowest index wins ties (tf.argmax)
-        float best = s0;
-        int bi = lane < C2 ? 2 * lane : 0x7fffffff;
-        if (s1 > best) { best = s1; bi = 2 * lane + 1; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (lane == 0) label[rowbase + x] = bi;
-        if (prob) {  // softmax_high_dimension, network.py:474-488
-            const float e0 = lane < C2 ? expf(s0 - best) : 0.f, e1 = lane < C2 ? expf(s1 - best) : 0.f;
-            float sum = e0 + e1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane < C2) *reinterpret_cast<float2*>(prob + (rowbase + x) * C + 2 * lane) = make_float2(e0 / sum, e1 / sum);
+    }
+    __syncthreads();
+    // arg-max over classes, lowest index wins ties (tf.argmax); softmax for prob_normalized (network.py:474-488)
+    for (int x = t; x < W; x += 256) {
+        const float* s = sc + x * C;
+        float best = s[0];
+        int bi = 0;
+        for (int c = 1; c < C; c++)
+            if (s[c] > best) { best = s[c]; bi = c; }
+        label[rowbase + x] = bi;
+        if (prob) {
+            float sum = 0.f;
+            for (int c = 0; c < C; c++) sum += expf(s[c] - best);
+            float* pr = prob + (rowbase + x) * C;
+            for (int c = 0; c < C; c++) pr[c] = expf(s[c] - best) / sum;
         }
     }
 }
@@ -239,8 +246,8 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
     PCNN_REQUIRE(lowres && bias_score && bias_vertex && label && vertex, "up8_heads: NULL tensor pointer");
     PCNN_REQUIRE(C >= 1 && B >= 1 && h >= 1 && w >= 1, "up8_heads: bad shape");
     PCNN_REQUIRE(8 * h <= 65535 * 1 && B <= 65535, "up8_heads: image too tall for the launch grid");
-    PCNN_REQUIRE(C % 2 == 0 && C <= 64, "up8_heads: num_classes must be even and <= 64 (got %d)", C);
-    size_t smem = sizeof(float) * ((size_t)w * 4 * C + 4 * C);
+    PCNN_REQUIRE(C % 2 == 0 && 2 * C <= 256, "up8_heads: num_classes must be even and <= 128 (got %d)", C);
+    size_t smem = sizeof(float) * ((size_t)w * 4 * C + (size_t)8 * w * C);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: row does not fit shared memory (w = %d, C = %d)", w, C);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_up8_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }

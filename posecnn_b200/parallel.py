@@ -27,8 +27,8 @@ def pack_records(layers: dict, num_classes: int, rank: int, local_batch: int) ->
     if "poses_tanh" in layers:
         rec[:, 14:14 + 4 * num_classes] = layers["poses_tanh"][:n]
     valid = torch.arange(n, device=rois.device) < layers["num_rois"].to(torch.int64)
-    rec[:, -1] = valid.float()
-    rec[:, 0] *= rec[:, -1]
+    rec[:, -1] = 1.0
+    rec *= valid.float()[:, None]  # rows beyond num_rois are all-zero (valid flag 0)
     return rec
 
 

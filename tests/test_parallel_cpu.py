@@ -1,0 +1,65 @@
+"""Multi-process path on CPU (gloo, world_size 2): record packing and the all-gather of per-rank
+pose-hypothesis records (posecnn_b200/parallel.py).  The GPU path uses the same code over NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from posecnn_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _fake_layers(rank, C, cap_rows, n_valid):
+    g = torch.Generator().manual_seed(100 + rank)
+    rois = torch.zeros((cap_rows, 7))
+    rois[:n_valid, 0] = torch.arange(n_valid) % 4                      # local batch index
+    rois[:n_valid, 1] = torch.randint(1, C, (n_valid,), generator=g).float()
+    rois[:n_valid, 2:] = torch.rand((n_valid, 5), generator=g) * 100
+    return dict(rois_capacity=rois, num_rois=torch.tensor([n_valid], dtype=torch.int32),
+                poses_init=torch.rand((cap_rows, 7), generator=g), poses_tanh=torch.rand((cap_rows, 4 * C), generator=g))
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    C, cap, local_batch = 6, 16, 4
+    L = _fake_layers(rank, C, cap, n_valid=5 + 3 * rank)
+    rec = parallel.pack_records(L, C, rank, local_batch)
+    allrec = parallel.all_gather_records(rec, world)
+    torch.save(dict(rec=rec, allrec=allrec), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_records_gloo_world2(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    C, cap, local_batch = 6, 16, 4
+    outs = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
+    assert torch.equal(outs[0]["allrec"], outs[1]["allrec"])           # every rank holds the same gathered table
+    allrec = outs[0]["allrec"]
+    assert allrec.shape == (world * cap, parallel.record_width(C))
+    for r in range(world):
+        blk = allrec[r * cap:(r + 1) * cap]
+        assert torch.equal(blk, outs[r]["rec"])
+        n_valid = 5 + 3 * r
+        assert blk[:, -1].sum().item() == n_valid and not blk[n_valid:, :14].any()
+        L = _fake_layers(r, C, cap, n_valid)
+        # batch indices are made global: rank * local_batch + local index
+        np.testing.assert_array_equal(blk[:n_valid, 0].numpy(), (L["rois_capacity"][:n_valid, 0] + r * local_batch).numpy())
+        assert torch.equal(blk[:n_valid, 1:7], L["rois_capacity"][:n_valid, 1:7])
+        assert torch.equal(blk[:n_valid, 14:14 + 4 * C], L["poses_tanh"][:n_valid])
+
+
+def test_pack_records_single_process():
+    L = _fake_layers(0, 4, 8, 3)
+    rec = parallel.pack_records(L, 4, rank=2, local_batch=32)
+    assert rec.shape == (8, parallel.record_width(4))
+    assert rec[:3, 0].tolist() == [64.0, 65.0, 66.0] and rec[3:, 0].abs().sum() == 0
+    assert parallel.all_gather_records(rec, 1) is rec
