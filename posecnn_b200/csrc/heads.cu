@@ -38,9 +38,12 @@ __host__ __device__ inline float deconv_w(int x, int k)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_lowres_heads: 8 low-resolution pixels per CTA
+// k_lowres_heads: one warp per pair of low-resolution pixels.  Lanes first build the two "add" vectors
+// (conv4 branch + 4x4/2 transposed convolution of the conv5 branch, coalesced bf16 reads) in the warp's
+// shared-memory slot, then every lane owns up to three of the 4C outputs and runs the two small matrix
+// products out of shared memory (weights conflict-free over lanes, activations broadcast).
 // ---------------------------------------------------------------------------------------------
-constexpr int kLrPix = 16;
+constexpr int kLrWarps = 8;
 
 __global__ void __launch_bounds__(256)
 k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_bfloat16* __restrict__ s5 /*[B,h/2,w/2,Cs]*/,
@@ -52,60 +55,71 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
     const int Ct = Cs + Cv;        // channels of the two "add" tensors
     const int No = 4 * C;          // outputs per pixel
     float* sW = sm;                // [Cs*C + Cv*3C]
-    float* sx = sm + Cs * C + Cv * 3 * C;  // [kLrPix][Ct]
+    float* sx_all = sm + Cs * C + Cv * 3 * C;  // [kLrWarps][2][Ct]
     for (int i = threadIdx.x; i < Cs * C; i += blockDim.x) sW[i] = Ws[i];
     for (int i = threadIdx.x; i < Cv * 3 * C; i += blockDim.x) sW[Cs * C + i] = Wv[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* sx = sx_all + warp * 2 * Ct;
     const int npix = B * h * w;
     const int h5 = h / 2, w5 = w / 2;
-    for (int p0 = blockIdx.x * kLrPix; p0 < npix; p0 += gridDim.x * kLrPix) {
-        __syncthreads();
-        // add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
-        for (int i = threadIdx.x; i < kLrPix * Ct; i += blockDim.x) {
-            const int pi = i / Ct, ch = i % Ct;
-            const int p = p0 + pi;
-            float val = 0.f;
-            if (p < npix) {
-                const int x = p % w, y = (p / w) % h;
-                const int n = p / (w * h);
+    const int npairs = (npix + 1) / 2;
+    for (int pr = blockIdx.x * kLrWarps + warp; pr < npairs; pr += gridDim.x * kLrWarps) {
+        // ---- add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int p = 2 * pr + q;
+            if (p >= npix) { for (int ch = lane; ch < Ct; ch += 32) sx[q * Ct + ch] = 0.f; continue; }
+            const int x = p % w, y = (p / w) % h, n = p / (w * h);
+            // out[o] += in[i] * W[o - 2 i + 1], 0 <= o - 2i + 1 <= 3: two source rows / columns
+            const int iy0 = ((y + 1) >> 1) - 1, ix0 = ((x + 1) >> 1) - 1;
+            float wgt[4];
+            size_t off5[4];
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const int iy = iy0 + (d >> 1), ix = ix0 + (d & 1);
+                const int ky = y - 2 * iy + 1, kx = x - 2 * ix + 1;
+                const bool ok = iy >= 0 && iy < h5 && ix >= 0 && ix < w5;
+                wgt[d] = ok ? deconv_w(ky, 4) * deconv_w(kx, 4) : 0.f;
+                off5[d] = ((size_t)(n * h5 + min(max(iy, 0), h5 - 1)) * w5 + min(max(ix, 0), w5 - 1));
+            }
+            for (int ch = lane; ch < Ct; ch += 32) {
                 const bool vert = ch >= Cs;
                 const int cc = vert ? ch - Cs : ch, Cn = vert ? Cv : Cs;
                 const __nv_bfloat16* a = vert ? v4 : s4;
                 const __nv_bfloat16* b5 = vert ? v5 : s5;
-                val = __bfloat162float(a[(size_t)p * Cn + cc]);
-                // out[o] += in[i] * W[o - 2 i + 1], 0 <= o - 2i + 1 <= 3
-                const int iy0 = ((y + 1) >> 1) - 1, ix0 = ((x + 1) >> 1) - 1;
-                float up = 0.f;
-#pragma unroll
-                for (int dy = 0; dy < 2; dy++) {
-                    const int iy = iy0 + dy, ky = y - 2 * iy + 1;
-                    if (iy < 0 || iy >= h5 || ky < 0 || ky > 3) continue;
-#pragma unroll
-                    for (int dx = 0; dx < 2; dx++) {
-                        const int ix = ix0 + dx, kx = x - 2 * ix + 1;
-                        if (ix < 0 || ix >= w5 || kx < 0 || kx > 3) continue;
-                        up += deconv_w(ky, 4) * deconv_w(kx, 4) * __bfloat162float(b5[((size_t)(n * h5 + iy) * w5 + ix) * Cn + cc]);
-                    }
-                }
-                val += up;
+                float up = wgt[0] * __bfloat162float(b5[off5[0] * Cn + cc]);
+                up = fmaf(wgt[1], __bfloat162float(b5[off5[1] * Cn + cc]), up);
+                up = fmaf(wgt[2], __bfloat162float(b5[off5[2] * Cn + cc]), up);
+                up = fmaf(wgt[3], __bfloat162float(b5[off5[3] * Cn + cc]), up);
+                sx[q * Ct + ch] = __bfloat162float(a[(size_t)p * Cn + cc]) + up;
             }
-            sx[i] = val;
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < kLrPix * No; i += blockDim.x) {
-            const int pi = i / No, o = i % No;
-            const int p = p0 + pi;
-            if (p >= npix) continue;
-            float acc = 0.f;
+        __syncwarp();
+        // ---- outputs o = lane, lane + 32, lane + 64, ... for both pixels
+        for (int o = lane; o < No; o += 32) {
+            float a0 = 0.f, a1 = 0.f;
             if (o < C) {
-                const float* x = sx + pi * Ct;
-                for (int k = 0; k < Cs; k++) acc = fmaf(x[k], sW[k * C + o], acc);
+                const float* wp = sW + o;
+                for (int k = 0; k < Cs; k++) {
+                    const float wk = wp[k * C];
+                    a0 = fmaf(sx[k], wk, a0);
+                    a1 = fmaf(sx[Ct + k], wk, a1);
+                }
             } else {
-                const float* x = sx + pi * Ct + Cs;
-                const float* wv = sW + Cs * C + (o - C);
-                for (int k = 0; k < Cv; k++) acc = fmaf(x[k], wv[k * 3 * C], acc);
+                const float* wp = sW + Cs * C + (o - C);
+                const int ld = 3 * C;
+                for (int k = 0; k < Cv; k++) {
+                    const float wk = wp[k * ld];
+                    a0 = fmaf(sx[Cs + k], wk, a0);
+                    a1 = fmaf(sx[Ct + Cs + k], wk, a1);
+                }
             }
-            out[(size_t)p * No + o] = acc;
+            const int p0 = 2 * pr;
+            out[(size_t)p0 * No + o] = a0;
+            if (p0 + 1 < npix) out[(size_t)(p0 + 1) * No + o] = a1;
         }
+        __syncwarp();
     }
 }
 
@@ -227,13 +241,13 @@ extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const v
 {
     PCNN_REQUIRE(score4 && score5 && vert4 && vert5 && w_score && w_vertex && out, "lowres_heads: NULL tensor pointer");
     PCNN_REQUIRE(h % 2 == 0 && w % 2 == 0, "lowres_heads: conv4 resolution must be even (got %d x %d)", h, w);
-    size_t smem = sizeof(float) * ((size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrPix * (Cs + Cv));
+    size_t smem = sizeof(float) * ((size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrWarps * 2 * (Cs + Cv));
     PCNN_REQUIRE(smem <= 200 * 1024, "lowres_heads: weights do not fit shared memory");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lowres_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     PCNN_REQUIRE((long long)B * h * w < 0x7fffffffLL, "lowres_heads: too many pixels");
     size_t npix = (size_t)B * h * w;
-    int blocks = (int)std::min<size_t>((npix + kLrPix - 1) / kLrPix, (size_t)kNumSMs * 4);
+    int blocks = (int)std::min<size_t>((npix + 2 * kLrWarps - 1) / (2 * kLrWarps), (size_t)kNumSMs * 4);
     k_lowres_heads<<<blocks, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)score4, (const __nv_bfloat16*)score5,
                                                                (const __nv_bfloat16*)vert4, (const __nv_bfloat16*)vert5, w_score,
                                                                w_vertex, B, h, w, Cs, Cv, C, out);

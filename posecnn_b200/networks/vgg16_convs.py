@@ -93,21 +93,31 @@ class vgg16_convs:
         """Benchmark-harness helper: a randomly initialised net labels (almost) every pixel as foreground, which is
         not what the Hough layer sees in use.  Shift `score/biases[0]` so that about `background_fraction` of the
         pixels of this batch are labelled background (YCB-like fill).  Declared in bench.py's config."""
-        L = self.forward(data, meta_data, extents, want_prob=False, sync_rois=False)
+        self.forward(data, meta_data, extents, want_prob=False, sync_rois=False)
         C = self.num_classes
         B, H, W, _ = data.shape
-        score = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device)
         lab = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
         vert = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
-        # re-run the streaming head with the raw scores exposed
         lowres = self._last_lowres
-        check(lib().pcnn_up8_heads(ptr(lowres), ptr(self.params["score/biases"]), ptr(self.params["vertex_pred/biases"]), B,
-                                   H // 8, W // 8, C, ptr(lab), ptr(vert), ptr(None), ptr(score), stream()))
-        gap = (score[..., 1:].max(dim=-1).values - score[..., 0]).flatten()
-        sub = gap[:: max(1, gap.numel() // 2000000)]
-        shift = float(torch.kthvalue(sub, max(1, int(background_fraction * sub.numel()))).values)
-        self.params["score/biases"][0] += shift + 1e-3
-        return shift
+        bias = self.params["score/biases"]
+        base = float(bias[0])
+
+        def fg_fraction(b0):
+            bias[0] = b0
+            check(lib().pcnn_up8_heads(ptr(lowres), ptr(bias), ptr(self.params["vertex_pred/biases"]), B, H // 8, W // 8, C,
+                                       ptr(lab), ptr(vert), ptr(None), ptr(None), stream()))
+            return float((lab > 0).float().mean())
+
+        scale = float(lowres[..., :C].abs().max()) + 1.0
+        lo, hi = base - scale, base + scale          # foreground fraction decreases as the background bias grows
+        for _ in range(24):
+            mid = 0.5 * (lo + hi)
+            if fg_fraction(mid) > 1.0 - background_fraction:
+                lo = mid
+            else:
+                hi = mid
+        bias[0] = hi
+        return hi - base
 
     def load(self, data_dict: dict):
         """TF-name dictionary {layer: {'weights': ..., 'biases': ...}} (VGG16 .npy, network.py:71-107) or flat
