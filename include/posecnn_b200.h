@@ -154,6 +154,9 @@ int pcnn_average_distance_bwd(const float* top_diff, const float* bottom_diff, i
  */
 int pcnn_conv_bf16_tc(const void* in_bf16, const void* weights_bf16, const float* bias, void* out_bf16, int B,
                       int H, int W, int Cin, int Cout, int ksize, int relu, int block_n, void* stream);
+/* same with the following 2x2 / stride-2 max pool (network.py:303-310) fused into the epilogue: out = [B,H/2,W/2,Cout] */
+int pcnn_conv_pool_bf16_tc(const void* in_bf16, const void* weights_bf16, const float* bias, void* out_pooled_bf16,
+                           int B, int H, int W, int Cin, int Cout, int ksize, int relu, int block_n, void* stream);
 /* conv1_1 (Cin = 3): in [B,H,W,Cin] f32, weights HWIO [3,3,Cin,Cout] f32 -> out [B,H,W,Cout] bf16 */
 int pcnn_conv3x3_small_cin(const float* in, const float* weights_hwio, const float* bias, void* out_bf16, int B,
                            int H, int W, int Cin, int Cout, int relu, void* stream);

@@ -28,6 +28,17 @@ def conv_bf16(x: torch.Tensor, w_tc: torch.Tensor, bias: torch.Tensor, ksize: in
     return out
 
 
+def conv_pool_bf16(x: torch.Tensor, w_tc: torch.Tensor, bias: torch.Tensor, ksize: int, relu: bool, block_n: int = 0) -> torch.Tensor:
+    """conv + bias + ReLU + 2x2/2 max pool in one kernel: x [B,H,W,Cin] bf16 -> [B,H/2,W/2,Cout] bf16."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cin = x.shape
+    Cout = w_tc.shape[0]
+    out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.bfloat16, device=x.device)
+    check(lib().pcnn_conv_pool_bf16_tc(ptr(x), ptr(w_tc), ptr(bias), ptr(out), B, H, W, Cin, Cout, int(ksize), int(bool(relu)),
+                                       int(block_n), stream()))
+    return out
+
+
 def conv3x3_small_cin(x: torch.Tensor, w_hwio: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
     """conv1_1: x [B,H,W,3] f32, w [3,3,3,Cout] f32 -> [B,H,W,Cout] bf16."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()

@@ -176,6 +176,7 @@ struct ConvParams {
     int taps, ksize;          // 9 / 3 or 1 / 1
     int tiles_h, tiles_w, n_tiles_n, total_tiles;
     int relu;
+    int pool;                 // 1: the epilogue applies the 2x2 / stride-2 max pool and stores ONLY the pooled tensor
     const float* bias;
 };
 
@@ -192,7 +193,7 @@ struct SmemPlan {
 template <int BN>
 __global__ void __launch_bounds__(kThreadsConv, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
-          const __grid_constant__ CUtensorMap map_out, const ConvParams p)
+          const __grid_constant__ CUtensorMap map_out, const ConvParams p)  // map_out: box {64,16,8,1}, or {64,8,4,1} of the pooled tensor
 {
     using Plan = SmemPlan<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -318,14 +319,36 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
                             packed[q] = *reinterpret_cast<uint32_t*>(&b2);
                         }
                         const int piece = half * 4 + j;  // 16-byte piece index within the 128-byte row
-                        uint4* dst = reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4));
-                        *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (!p.pool) {
+                            uint4* dst = reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4));
+                            *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        } else {
+                            // fused max_pool 2x2/2 (network.py:303-310): tile row m = 16 h + w, a warp holds two image
+                            // rows; the 2x2 window of (h even, w even) lives in lanes l, l^1, l^16, l^17.  max on the
+                            // bf16 values = bf16 of the fp32 max (rounding is monotone).
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&packed[q]);
+                                uint32_t o1 = __shfl_xor_sync(0xffffffffu, packed[q], 1);
+                                v = __hmax2(v, *reinterpret_cast<__nv_bfloat162*>(&o1));
+                                uint32_t vv = *reinterpret_cast<uint32_t*>(&v);
+                                uint32_t o2 = __shfl_xor_sync(0xffffffffu, vv, 16);
+                                v = __hmax2(v, *reinterpret_cast<__nv_bfloat162*>(&o2));
+                                packed[q] = *reinterpret_cast<uint32_t*>(&v);
+                            }
+                            if ((lane & 17) == 0) {
+                                const int prow = warp * 8 + (lane >> 1);  // pooled tile: 4 rows x 8 cols, row = ph * 8 + pw
+                                uint4* dst = reinterpret_cast<uint4*>(ob + prow * 128 + ((piece ^ (prow & 7)) << 4));
+                                *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            }
+                        }
                     }
                 }
                 fence_proxy_async();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (threadIdx.x == 0) {
-                    tma_store_4d(&map_out, ob, n0 + g * 64, w0, h0, img);
+                    if (!p.pool) tma_store_4d(&map_out, ob, n0 + g * 64, w0, h0, img);
+                    else tma_store_4d(&map_out, ob, n0 + g * 64, w0 >> 1, h0 >> 1, img);
                     tma_store_commit();
                 }
                 obuf ^= 1;
@@ -480,13 +503,13 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
-static int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_c)
+static int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_c, int box_w = kTileW, int box_h = kTileH)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable (driver too old?)"); return PCNN_E_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, kTileW, kTileH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -534,8 +557,25 @@ using namespace pcnn::convtc;
 
 // in [B,H,W,Cin] bf16, weights [Cout][ksize*ksize*Cin] bf16 (tap-major, channel-minor), bias [Cout] f32,
 // out [B,H,W,Cout] bf16.  Cin % 64 == 0, Cout % 64 == 0, ksize in {1, 3}.
+static int conv_bf16_tc_impl(const void* in, const void* weights, const float* bias, void* out, int B, int H, int W, int Cin,
+                            int Cout, int ksize, int relu, int block_n, int pool, void* stream);
+
 extern "C" int pcnn_conv_bf16_tc(const void* in, const void* weights, const float* bias, void* out, int B, int H, int W,
                                  int Cin, int Cout, int ksize, int relu, int block_n, void* stream)
+{
+    return conv_bf16_tc_impl(in, weights, bias, out, B, H, W, Cin, Cout, ksize, relu, block_n, 0, stream);
+}
+
+// conv + bias + ReLU + 2x2/2 max pool fused: out is the POOLED tensor [B,H/2,W/2,Cout] bf16 (H, W even)
+extern "C" int pcnn_conv_pool_bf16_tc(const void* in, const void* weights, const float* bias, void* out_pooled, int B, int H,
+                                      int W, int Cin, int Cout, int ksize, int relu, int block_n, void* stream)
+{
+    PCNN_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv_pool: needs even H, W (got %d x %d)", H, W);
+    return conv_bf16_tc_impl(in, weights, bias, out_pooled, B, H, W, Cin, Cout, ksize, relu, block_n, 1, stream);
+}
+
+static int conv_bf16_tc_impl(const void* in, const void* weights, const float* bias, void* out, int B, int H, int W, int Cin,
+                            int Cout, int ksize, int relu, int block_n, int pool, void* stream)
 {
     PCNN_REQUIRE(in && weights && bias && out, "conv: NULL tensor pointer");
     PCNN_REQUIRE(ksize == 1 || ksize == 3, "conv: ksize must be 1 or 3 (got %d)", ksize);
@@ -550,7 +590,7 @@ extern "C" int pcnn_conv_bf16_tc(const void* in, const void* weights, const floa
     if (rc) return rc;
     rc = make_map_weights(&mw, weights, ksize * ksize * Cin, Cout, bn);
     if (rc) return rc;
-    rc = make_map_nhwc(&mo, out, B, H, W, Cout, 64);
+    rc = pool ? make_map_nhwc(&mo, out, B, H / 2, W / 2, Cout, 64, kTileW / 2, kTileH / 2) : make_map_nhwc(&mo, out, B, H, W, Cout, 64);
     if (rc) return rc;
     ConvParams p;
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -560,6 +600,7 @@ extern "C" int pcnn_conv_bf16_tc(const void* in, const void* weights, const floa
     p.n_tiles_n = Cout / bn;
     p.total_tiles = B * p.tiles_h * p.tiles_w * p.n_tiles_n;
     p.relu = relu;
+    p.pool = pool;
     p.bias = bias;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

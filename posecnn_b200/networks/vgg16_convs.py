@@ -159,14 +159,24 @@ class vgg16_convs:
         x = conv.im2col_c3(data, mean)
         x = conv.conv_bf16(x, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], 1, True)
         feats = {}
-        for item in VGG_CFG[1:]:
+        cfg = VGG_CFG[1:]
+        i = 0
+        while i < len(cfg):
+            item = cfg[i]
             if isinstance(item, str):
                 x = conv.maxpool2x2(x)
-            else:
-                name = item[0]
-                x = conv.conv_bf16(x, T[f"{name}{sfx}/weights"], P[f"{name}{sfx}/biases"], 3, True)
-                if name in ("conv4_3", "conv5_3"):
-                    feats[name] = x
+                i += 1
+                continue
+            name = item[0]
+            fuse_pool = i + 1 < len(cfg) and isinstance(cfg[i + 1], str) and name not in ("conv4_3", "conv5_3")
+            if fuse_pool:   # conv + ReLU + max-pool in one kernel (the un-pooled tensor is not needed downstream)
+                x = conv.conv_pool_bf16(x, T[f"{name}{sfx}/weights"], P[f"{name}{sfx}/biases"], 3, True)
+                i += 2
+                continue
+            x = conv.conv_bf16(x, T[f"{name}{sfx}/weights"], P[f"{name}{sfx}/biases"], 3, True)
+            if name in ("conv4_3", "conv5_3"):
+                feats[name] = x
+            i += 1
         return feats
 
     def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True):

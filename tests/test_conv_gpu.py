@@ -60,3 +60,19 @@ def test_conv_small_cin_and_maxpool(cuda):
     p = conv.maxpool2x2(y)
     wantp = F.max_pool2d(y.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     assert torch.equal(p.float(), wantp)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(2, 24, 48, 64, 64, 64), (1, 30, 44, 128, 128, 128), (1, 16, 32, 256, 256, 256),
+                                             (2, 60, 80, 64, 128, 0)])
+def test_conv_pool_fused(cuda, B, H, W, Cin, Cout, bn):
+    """conv + bias + ReLU + 2x2/2 max pool fused in the epilogue == un-fused conv followed by the pool kernel (bit exact)."""
+    from posecnn_b200 import conv
+    g = torch.Generator(device="cpu").manual_seed(99 + H)
+    x = torch.randn((B, H, W, Cin), generator=g).to(torch.bfloat16).to(cuda)
+    w = conv.hwio_to_tc((torch.randn((3, 3, Cin, Cout), generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(cuda))
+    bias = torch.randn((Cout,), generator=g).to(cuda)
+    want = conv.maxpool2x2(conv.conv_bf16(x, w, bias, 3, True, bn))
+    got = conv.conv_pool_bf16(x, w, bias, 3, True, bn)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
