@@ -164,6 +164,10 @@ int pcnn_conv3x3_small_cin(const float* in, const float* weights_hwio, const flo
  * pre-processing of lib/fcn/test.py:37-110 fused) -> [B,H,W,64] bf16 with K = tap*3 + c, then a 1x1 pcnn_conv_bf16_tc */
 int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_host, void* out_bf16, int B, int H, int W,
                    void* stream);
+/* conv1_1 with the im2col built in shared memory (no HBM round trip): in [B,H,W,3] u8 (minus mean) or f32,
+ * weights [64][64] bf16 in the K order tap*3 + c (zero padded), bias [64] -> out [B,H,W,64] bf16 */
+int pcnn_conv1_fused_tc(const void* in, int in_is_u8, const float* mean3_host, const void* weights_bf16,
+                        const float* bias, void* out_bf16, int B, int H, int W, int relu, void* stream);
 int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -75,3 +75,16 @@ def conv1_1_weights_to_tc(w_hwio: torch.Tensor) -> torch.Tensor:
     w = torch.zeros((co, 64), dtype=torch.float32, device=w_hwio.device)
     w[:, :27] = w_hwio.reshape(27, co).t()
     return w.to(torch.bfloat16).contiguous()
+
+
+def conv1_fused(x: torch.Tensor, w_tc64: torch.Tensor, bias: torch.Tensor, mean=None, relu: bool = True) -> torch.Tensor:
+    """conv1_1 in one kernel: x [B,H,W,3] u8 / f32, w_tc64 = conv1_1_weights_to_tc(w) [64,64] bf16 -> [B,H,W,64] bf16."""
+    import ctypes
+    assert x.is_cuda and x.is_contiguous() and x.shape[3] == 3 and x.dtype in (torch.float32, torch.uint8)
+    assert w_tc64.shape == (64, 64) and w_tc64.dtype == torch.bfloat16
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=x.device)
+    m = (ctypes.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+    check(lib().pcnn_conv1_fused_tc(ptr(x), int(x.dtype == torch.uint8), m, ptr(w_tc64), ptr(bias), ptr(out), B, H, W,
+                                    int(bool(relu)), stream()))
+    return out

@@ -366,6 +366,177 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------
+// First layer (conv1_1, Cin = 3, K = 27 -> 32) on the tensor cores with the im2col done in shared memory:
+// warps 4-7 build the A tile of an 8x16 pixel tile straight from the uint8 / f32 image (pre-processing
+// `BGR - PIXEL_MEANS` fused, zero outside the image = SAME padding) in the swizzled K-major layout, warp 8
+// issues two K = 16 UMMAs per tile against the resident 64 x 64 weight tile, warps 0-3 run the usual
+// epilogue.  No im2col tensor ever exists in HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kC1Stages = 6;
+constexpr int kC1Threads = 288;
+constexpr int kC1BarOff = kC1Stages * kABytes + 64 * 128 + 2 * kStageBytes;
+constexpr int kC1Smem = kC1BarOff + 256 + 1024;
+
+template <typename TIn>
+__global__ void __launch_bounds__(kC1Threads, 1)
+k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+           const ConvParams p, float m0, float m1, float m2)
+{
+    constexpr int BN = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sb = smem + kC1Stages * kABytes;          // weights: 64 rows x 128 B, swizzled (TMA)
+    uint8_t* out_stage = sb + 64 * 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kC1BarOff);
+    uint64_t* empty = full + kC1Stages;
+    uint64_t* tfull = empty + kC1Stages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wbar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BN;
+
+    if (warp == 8 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        for (int s = 0; s < kC1Stages; s++) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_holder, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp >= 4 && warp < 8) {
+        // ===================== A builders: one tile row (pixel) per thread =====================
+        const int r = threadIdx.x - 128;
+        const int hl = r >> 4, wl = r & 15;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w;
+            const int rest = tile / p.tiles_w;
+            const int th = rest % p.tiles_h, img = rest / p.tiles_h;
+            const int y = th * kTileH + hl, x = tw * kTileW + wl;
+            const TIn* base = in + (size_t)img * p.H * p.W * 3;
+            float v[32];
+#pragma unroll
+            for (int k = 27; k < 32; k++) v[k] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                const int yy = y + dy - 1;
+                const bool rowok = yy >= 0 && yy < p.H;
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int xx = x + dx - 1;
+                    const bool ok = rowok && xx >= 0 && xx < p.W;
+                    const TIn* px = base + ((size_t)yy * p.W + xx) * 3;
+                    v[(dy * 3 + dx) * 3 + 0] = ok ? (float)px[0] - m0 : 0.f;
+                    v[(dy * 3 + dx) * 3 + 1] = ok ? (float)px[1] - m1 : 0.f;
+                    v[(dy * 3 + dx) * 3 + 2] = ok ? (float)px[2] - m2 : 0.f;
+                }
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kABytes + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j * 8 + q * 2], v[j * 8 + q * 2 + 1]);
+                    pk[q] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(sa + ((j ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer (+ one-time weight load) =====================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(wbar, 64 * 128);
+            tma_load_2d(sb, &map_w, wbar, 0, 0);
+            mbar_wait(wbar, 0);
+            constexpr uint32_t idesc = make_idesc(BN);
+            const uint64_t db = make_desc(smem_u32(sb));
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint64_t da = make_desc(smem_u32(smem + stage * kABytes));
+                umma_bf16(tmem_base + acc * BN, da, db, idesc, 0);            // K 0..15
+                umma_bf16(tmem_base + acc * BN, da + 2, db + 2, idesc, 1);    // K 16..31 (27..31 are zero)
+                umma_commit(&empty[stage]);
+                umma_commit(&tfull[acc]);
+                if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps 0..3 (same as k_conv_tc, BN = 64) =====================
+        int it = 0, obuf = 0;
+        const int row = warp * 32 + lane;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            const int tw = tile % p.tiles_w;
+            const int rest = tile / p.tiles_w;
+            const int th = rest % p.tiles_h, img = rest / p.tiles_h;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+            if (threadIdx.x == 0) tma_store_wait_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            uint8_t* ob = out_stage + obuf * kStageBytes;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t rr[32];
+                tmem_ld_32x32(t_addr + half * 32, rr);
+                tmem_ld_wait();
+                const float* bias = p.bias + half * 32;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        float v0 = __uint_as_float(rr[j * 8 + q * 2]) + __ldg(bias + j * 8 + q * 2);
+                        float v1 = __uint_as_float(rr[j * 8 + q * 2 + 1]) + __ldg(bias + j * 8 + q * 2 + 1);
+                        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                        packed[q] = *reinterpret_cast<uint32_t*>(&b2);
+                    }
+                    const int piece = half * 4 + j;
+                    *reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+                tma_store_4d(&map_out, ob, 0, tw * kTileW, th * kTileH, img);
+                tma_store_commit();
+            }
+            obuf ^= 1;
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // conv1_1 (Cin = 3, K = 27: below any tensor-core tile) on the CUDA cores, fused with the input
 // pre-processing-free path: fp32 NHWC in, bf16 NHWC out, bias + ReLU.  One thread = one pixel x 16
 // output channels; the 27 x Cout weights sit in shared memory.
@@ -650,4 +821,41 @@ extern "C" int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_h
     else
         k_im2col_c3<float><<<grid, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out_bf16, H, W, m0, m1, m2);
     return check_launch("im2col_c3");
+}
+
+// conv1_1 fused: in [B,H,W,3] (u8 minus mean, or f32), weights [64][64] bf16 in im2col K order (tap*3 + c, zero padded),
+// bias [64] f32 -> out [B,H,W,64] bf16.  Replaces pcnn_im2col_c3 + a 1x1 pcnn_conv_bf16_tc without the HBM round trip.
+extern "C" int pcnn_conv1_fused_tc(const void* in, int in_is_u8, const float* mean3_host, const void* weights_bf16,
+                                   const float* bias, void* out_bf16, int B, int H, int W, int relu, void* stream)
+{
+    PCNN_REQUIRE(in && weights_bf16 && bias && out_bf16, "conv1: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1, "conv1: bad shape");
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    if (mean3_host) { m0 = mean3_host[0]; m1 = mean3_host[1]; m2 = mean3_host[2]; }
+    CUtensorMap mw, mo;
+    int rc = make_map_weights(&mw, weights_bf16, 64, 64, 64);
+    if (rc) return rc;
+    rc = make_map_nhwc(&mo, out_bf16, B, H, W, 64, 64);
+    if (rc) return rc;
+    ConvParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = 3; p.Cout = 64; p.ksize = 3; p.taps = 9;
+    p.tiles_h = (H + kTileH - 1) / kTileH;
+    p.tiles_w = (W + kTileW - 1) / kTileW;
+    p.n_tiles_n = 1;
+    p.total_tiles = B * p.tiles_h * p.tiles_w;
+    p.relu = relu; p.pool = 0; p.bias = bias;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_conv1_tc<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
+        cudaFuncSetAttribute(k_conv1_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
+        attr = true;
+    }
+    if (in_is_u8) k_conv1_tc<unsigned char><<<grid, kC1Threads, kC1Smem, st>>>((const unsigned char*)in, mw, mo, p, m0, m1, m2);
+    else k_conv1_tc<float><<<grid, kC1Threads, kC1Smem, st>>>((const float*)in, mw, mo, p, m0, m1, m2);
+    return check_launch("conv1_fused_tc");
 }

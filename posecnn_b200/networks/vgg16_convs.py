@@ -156,8 +156,7 @@ class vgg16_convs:
         subtracted on the fly) or f32 (already pre-processed)."""
         P, T = self.params, self._tc
         mean = PIXEL_MEANS if data.dtype == torch.uint8 else None
-        x = conv.im2col_c3(data, mean)
-        x = conv.conv_bf16(x, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], 1, True)
+        x = conv.conv1_fused(data, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], mean, True)
         feats = {}
         cfg = VGG_CFG[1:]
         i = 0

@@ -76,3 +76,24 @@ def test_conv_pool_fused(cuda, B, H, W, Cin, Cout, bn):
     torch.cuda.synchronize()
     assert got.shape == want.shape
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_conv1_fused_matches_im2col_path(cuda, dtype):
+    """conv1_1 with the im2col built in shared memory == im2col kernel + 1x1 tensor-core conv (bit exact) == fp32 reference."""
+    from posecnn_b200 import conv
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W = 2, 37, 53
+    x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(cuda) if dtype == torch.uint8 else \
+        torch.randn((B, H, W, 3), generator=g).to(cuda)
+    mean = (102.9801, 115.9465, 122.7717) if dtype == torch.uint8 else None
+    w = (torch.randn((3, 3, 3, 64), generator=g) * 0.2).to(cuda)
+    b = torch.randn((64,), generator=g).to(cuda)
+    wt = conv.conv1_1_weights_to_tc(w)
+    got = conv.conv1_fused(x, wt, b, mean, True)
+    want = conv.conv_bf16(conv.im2col_c3(x, mean), wt, b, 1, True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    xf = x.float() - (torch.tensor(mean, device=cuda) if mean else 0.0)
+    ref = ref_conv(xf.to(torch.bfloat16), w.to(torch.bfloat16), b, True)
+    assert ((got.float() - ref).abs() <= 2 ** -7 * ref.abs().clamp(min=1.0)).all()
