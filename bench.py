@@ -81,6 +81,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("PCNN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -198,7 +199,7 @@ def run_hough(args, rank, world, local):
 # labels, SURVEY finding 10), synthetic uint8 images.
 # ------------------------------------------------------------------------------------------
 VGG_FLOP_PER_FRAME = 187.918e9  # sum of 2*M*K*N over conv1_1..conv5_3
-LAUNCHES_FULL = 18 + 6 + 7 + 2   # trunk (im2col, 13 conv, 4 pool) + heads (4 conv, lowres, up8) + hough (7) + roi_pool (2)
+LAUNCHES_FULL = 14 + 6 + 7 + 2   # trunk (conv1 fused, 12 conv of which 3 with fused pool, pool4) + heads (4 conv, lowres, up8) + hough (7) + roi_pool (2)
 
 
 def run_full(args, rank, world, local):

@@ -18,6 +18,7 @@
 //     MMA issuer; persistent CTAs, one per SM, static round-robin tile schedule.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -354,6 +355,265 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
                 obuf ^= 1;
             }
             // all TMEM reads of this accumulator stage are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row mode for the K-small layers (conv1_2, conv2_x: Cin, Cout <= 128), which are bound by L2 -> SM operand
+// traffic in the tile kernel (every tap re-fetches its A tile; profiles/r01_conv_tc_ncu_full.txt).
+// A work item is TWO output rows x 128 pixels of one image:
+//   * per 64-channel chunk ONE TMA box {64 ch, 130 px, 4 rows} (halo included) is loaded; the A operand of
+//     tap (r, s) for output row j is the 128 consecutive patch rows starting at ((r + j) * 130 + s): a
+//     row-shifted view of the same shared-memory patch (the UMMA swizzle is a function of the shared-memory
+//     address, so a start address that is 128-B but not 1024-B aligned needs no descriptor change — checked on
+//     hardware with tools/probe/umma_probe.cu);
+//   * every weight stage feeds both output rows (two accumulators), halving the weight traffic as well;
+//   * the two rows of a pair are exactly the rows a 2x2 max pool combines, so the pool stays fused: vertical
+//     max in registers (both rows live in the same TMEM lane), horizontal max by shuffle.
+// Operand bytes per 128 output pixels drop from 9 * (16 + BN/8) KB to (32.5 + 4.5 * BN/8) KB per chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowPx = 128, kPatchW = 130, kPatchH = 4;
+constexpr int kPatchBytes = kPatchW * kPatchH * 128;  // 66,560 = 65 * 1024
+constexpr int kRowAStages = 2;
+
+// RESB (Cin = 64, BN = 64 only): the nine 8-KB weight slices of the CTA's N tile stay resident in shared memory for
+// the whole kernel (a 48-KB ring cannot keep enough weight bytes in flight to hide the L2 latency); every CTA keeps
+// one N tile (nt = blockIdx.x % n_tiles_n).  The epilogue staging shrinks to 16 KB to make room.
+template <int BN, bool RESB>
+struct RowPlan {
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kBStages = RESB ? 9 : (BN == 64 ? 6 : 3);
+    static constexpr int kBOff = kRowAStages * kPatchBytes;
+    static constexpr int kOutOff = kBOff + kBStages * kBBytes;
+    static constexpr int kOutBytes = RESB ? kStageBytes : 2 * kStageBytes;
+    static constexpr int kBarOff = kOutOff + kOutBytes;
+    static constexpr int kTotal = kBarOff + 256 + 1024;
+};
+
+template <int BN, bool RESB>
+__global__ void __launch_bounds__(kThreadsConv, 1)
+k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, const __grid_constant__ CUtensorMap map_w,
+            const __grid_constant__ CUtensorMap map_out /*box {64,128,1,1}, or {64,64,1,1} of the pooled tensor*/,
+            const ConvParams p)
+{
+    using Plan = RowPlan<BN, RESB>;
+    static_assert(!RESB || BN == 64, "resident weights: BN = 64 only");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem + Plan::kBOff;
+    uint8_t* out_stage = smem + Plan::kOutOff;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Plan::kBarOff);
+    uint64_t* emptyA = fullA + kRowAStages;
+    uint64_t* fullB = emptyA + kRowAStages;
+    uint64_t* emptyB = fullB + Plan::kBStages;
+    uint64_t* tfull = emptyB + Plan::kBStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wbar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / kKC;
+    constexpr uint32_t kTmemCols = 4 * BN;
+    // work items of this CTA: RESB -> fixed N tile, spatial tiles strided; otherwise all (spatial, N) tiles strided
+    const int tile0 = RESB ? blockIdx.x / p.n_tiles_n : blockIdx.x;
+    const int tstep = RESB ? gridDim.x / p.n_tiles_n : gridDim.x;
+    const int tcount = RESB ? p.total_tiles / p.n_tiles_n : p.total_tiles;
+    const int nt_fixed = blockIdx.x % p.n_tiles_n;  // 2 accumulator stages x 2 output rows
+    // tiles_h = row pairs, tiles_w = 128-pixel segments
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    }
+    if (warp == 5 && lane == 0) {
+        for (int s = 0; s < kRowAStages; s++) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < Plan::kBStages; s++) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_holder, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            if (RESB) {
+                mbar_arrive_expect_tx(wbar, 9 * Plan::kBBytes);
+                for (int tap = 0; tap < 9; tap++) tma_load_2d(sB + tap * Plan::kBBytes, &map_w, wbar, tap * p.Cin, nt_fixed * BN);
+            }
+            for (int tile = tile0; tile < tcount; tile += tstep) {
+                const int nt = RESB ? nt_fixed : tile % p.n_tiles_n;
+                int rest = RESB ? tile : tile / p.n_tiles_n;
+                const int tw = rest % p.tiles_w; rest /= p.tiles_w;
+                const int yp = rest % p.tiles_h;
+                const int img = rest / p.tiles_h;
+                const int y0 = 2 * yp, x0 = tw * kRowPx, n0 = nt * BN;
+                for (int c = 0; c < kchunks; c++) {
+                    mbar_wait(&emptyA[sa], pa ^ 1);
+                    mbar_arrive_expect_tx(&fullA[sa], kPatchBytes);
+                    tma_load_4d(smem + sa * kPatchBytes, &map_in, &fullA[sa], c * kKC, x0 - 1, y0 - 1, img);
+                    if (++sa == kRowAStages) { sa = 0; pa ^= 1; }
+                    if (!RESB) {
+                        for (int tap = 0; tap < 9; tap++) {
+                            mbar_wait(&emptyB[sb], pb ^ 1);
+                            mbar_arrive_expect_tx(&fullB[sb], Plan::kBBytes);
+                            tma_load_2d(sB + sb * Plan::kBBytes, &map_w, &fullB[sb], tap * p.Cin + c * kKC, n0);
+                            if (++sb == Plan::kBStages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            if (RESB) mbar_wait(wbar, 0);
+            for (int tile = tile0; tile < tcount; tile += tstep, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int c = 0; c < kchunks; c++) {
+                    mbar_wait(&fullA[sa], pa);
+                    const uint32_t a_base = smem_u32(smem + sa * kPatchBytes);
+                    for (int tap = 0; tap < 9; tap++) {
+                        if (!RESB) mbar_wait(&fullB[sb], pb);
+                        tc_fence_after();
+                        const int r = tap / 3, s = tap - 3 * r;
+                        const uint64_t db = make_desc(smem_u32(sB + (RESB ? tap : sb) * Plan::kBBytes));
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const uint64_t da = make_desc(a_base + (uint32_t)(((r + j) * kPatchW + s) * 128));
+                            const uint32_t d_tmem = tmem_base + (acc * 2 + j) * BN;
+#pragma unroll
+                            for (int k = 0; k < kKC / 16; k++)
+                                umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | tap | k) != 0);
+                        }
+                        if (!RESB) {
+                            umma_commit(&emptyB[sb]);
+                            if (++sb == Plan::kBStages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    umma_commit(&emptyA[sa]);
+                    if (++sa == kRowAStages) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue warps 0..3: thread = pixel x0 + row of both output rows =====================
+        int it = 0, obuf = 0;
+        const int row = warp * 32 + lane;
+        for (int tile = tile0; tile < tcount; tile += tstep, it++) {
+            const int nt = RESB ? nt_fixed : tile % p.n_tiles_n;
+            int rest = RESB ? tile : tile / p.n_tiles_n;
+            const int tw = rest % p.tiles_w; rest /= p.tiles_w;
+            const int yp = rest % p.tiles_h;
+            const int img = rest / p.tiles_h;
+            const int y0 = 2 * yp, x0 = tw * kRowPx, n0 = nt * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+            if (!p.pool) {
+#pragma unroll 1
+                for (int jg = 0; jg < 2 * (BN / 64); jg++) {
+                    const int j = jg / (BN / 64), g = jg % (BN / 64);
+                    if (threadIdx.x == 0) { if (RESB) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    uint8_t* ob = out_stage + (RESB ? 0 : obuf * kStageBytes);
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        uint32_t rr[32];
+                        tmem_ld_32x32(t_lane + (acc * 2 + j) * BN + g * 64 + half * 32, rr);
+                        tmem_ld_wait();
+                        const float* bias = p.bias + n0 + g * 64 + half * 32;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; q4++) {
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                float v0 = __uint_as_float(rr[q4 * 8 + q * 2]) + __ldg(bias + q4 * 8 + q * 2);
+                                float v1 = __uint_as_float(rr[q4 * 8 + q * 2 + 1]) + __ldg(bias + q4 * 8 + q * 2 + 1);
+                                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                                packed[q] = *reinterpret_cast<uint32_t*>(&b2);
+                            }
+                            const int piece = half * 4 + q4;
+                            *reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        }
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        tma_store_4d(&map_out, ob, n0 + g * 64, x0, y0 + j, img);
+                        tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < BN / 64; g++) {
+                    if (threadIdx.x == 0) tma_store_wait_read<1>();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    uint8_t* ob = out_stage + obuf * (RESB ? kStageBytes / 2 : kStageBytes);  // pooled tile: 64 rows = 8 KB
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld_32x32(t_lane + (acc * 2 + 0) * BN + g * 64 + half * 32, r0);
+                        tmem_ld_32x32(t_lane + (acc * 2 + 1) * BN + g * 64 + half * 32, r1);
+                        tmem_ld_wait();
+                        const float* bias = p.bias + n0 + g * 64 + half * 32;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; q4++) {
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float b0 = __ldg(bias + q4 * 8 + q * 2), b1 = __ldg(bias + q4 * 8 + q * 2 + 1);
+                                // vertical max of the pair (same bias, monotone ReLU / rounding: order is irrelevant)
+                                float v0 = fmaxf(__uint_as_float(r0[q4 * 8 + q * 2]), __uint_as_float(r1[q4 * 8 + q * 2])) + b0;
+                                float v1 = fmaxf(__uint_as_float(r0[q4 * 8 + q * 2 + 1]), __uint_as_float(r1[q4 * 8 + q * 2 + 1])) + b1;
+                                if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                                uint32_t pk = *reinterpret_cast<uint32_t*>(&b2);
+                                uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk, 1);  // horizontal neighbour x ^ 1
+                                b2 = __hmax2(b2, *reinterpret_cast<__nv_bfloat162*>(&o1));
+                                packed[q] = *reinterpret_cast<uint32_t*>(&b2);
+                            }
+                            if ((lane & 1) == 0) {
+                                const int prow = row >> 1;  // pooled pixel within the 64-wide pooled segment
+                                const int piece = half * 4 + q4;
+                                *reinterpret_cast<uint4*>(ob + prow * 128 + ((piece ^ (prow & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        tma_store_4d(&map_out, ob, n0 + g * 64, x0 >> 1, y0 >> 1, img);
+                        tma_store_commit();
+                    }
+                    obuf ^= 1;
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -720,6 +980,23 @@ static int launch_conv(const CUtensorMap& mi, const CUtensorMap& mw, const CUten
     return check_launch("conv_tc");
 }
 
+template <int BN, bool RESB>
+static int launch_conv_row2(const CUtensorMap& mi, const CUtensorMap& mw, const CUtensorMap& mo, const ConvParams& p, int num_sms,
+                            cudaStream_t st)
+{
+    using Plan = RowPlan<BN, RESB>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv_row2<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
+        if (e != cudaSuccess) { set_error("conv_row2<%d>: cannot reserve %d B of shared memory: %s", BN, Plan::kTotal, cudaGetErrorString(e)); return PCNN_E_CUDA; }
+        attr = true;
+    }
+    int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    if (RESB) grid = grid / p.n_tiles_n * p.n_tiles_n;  // every CTA owns one N tile
+    k_conv_row2<BN, RESB><<<grid, kThreadsConv, Plan::kTotal, st>>>(mi, mw, mo, p);
+    return check_launch("conv_row2");
+}
+
 }  // namespace convtc
 }  // namespace pcnn
 
@@ -756,8 +1033,36 @@ static int conv_bf16_tc_impl(const void* in, const void* weights, const float* b
     int bn = block_n;
     if (bn == 0) bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     PCNN_REQUIRE((bn == 64 || bn == 128 || bn == 256) && Cout % bn == 0, "conv: block_n %d does not divide Cout %d", bn, Cout);
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap mi, mw, mo;
-    int rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC);
+    int rc;
+    // row mode (two output rows x 128 px per work item, A patch reused by all nine taps) for the K-small layers
+    static const bool row_mode_on = getenv("PCNN_CONV_ROWMODE") == nullptr || atoi(getenv("PCNN_CONV_ROWMODE")) != 0;
+    if (row_mode_on && block_n == 0 && ksize == 3 && Cin <= 128 && Cout <= 128 && H % 2 == 0 && W >= kRowPx) {
+        // conv1_2 shape (Cin = Cout = 64): the nine 8-KB weight slices stay resident in shared memory (measured:
+        // 0.70 -> 0.65 ms); with two N tiles (conv2_1) the doubled A traffic costs more than the weight ring saves
+        const bool resb = Cin == 64 && Cout == 64;
+        bn = Cout;  // 64 or 128
+        rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC, kPatchW, kPatchH);
+        if (rc) return rc;
+        rc = make_map_weights(&mw, weights, 9 * Cin, Cout, bn);
+        if (rc) return rc;
+        rc = pool ? make_map_nhwc(&mo, out, B, H / 2, W / 2, Cout, 64, kRowPx / 2, 1) : make_map_nhwc(&mo, out, B, H, W, Cout, 64, kRowPx, 1);
+        if (rc) return rc;
+        ConvParams p;
+        p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = 3; p.taps = 9;
+        p.tiles_h = H / 2;
+        p.tiles_w = (W + kRowPx - 1) / kRowPx;
+        p.n_tiles_n = Cout / bn;
+        p.total_tiles = B * p.tiles_h * p.tiles_w * p.n_tiles_n;
+        p.relu = relu; p.pool = pool; p.bias = bias;
+        if (resb && p.total_tiles >= p.n_tiles_n) return launch_conv_row2<64, true>(mi, mw, mo, p, sms, st);
+        return bn == 128 ? launch_conv_row2<128, false>(mi, mw, mo, p, sms, st) : launch_conv_row2<64, false>(mi, mw, mo, p, sms, st);
+    }
+    rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC);
     if (rc) return rc;
     rc = make_map_weights(&mw, weights, ksize * ksize * Cin, Cout, bn);
     if (rc) return rc;
@@ -773,10 +1078,6 @@ static int conv_bf16_tc_impl(const void* in, const void* weights, const float* b
     p.relu = relu;
     p.pool = pool;
     p.bias = bias;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaStream_t st = (cudaStream_t)stream;
     if (bn == 256) return launch_conv<256>(mi, mw, mo, p, sms, st);
     if (bn == 128) return launch_conv<128>(mi, mw, mo, p, sms, st);
     return launch_conv<64>(mi, mw, mo, p, sms, st);

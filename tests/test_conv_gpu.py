@@ -97,3 +97,31 @@ def test_conv1_fused_matches_im2col_path(cuda, dtype):
     xf = x.float() - (torch.tensor(mean, device=cuda) if mean else 0.0)
     ref = ref_conv(xf.to(torch.bfloat16), w.to(torch.bfloat16), b, True)
     assert ((got.float() - ref).abs() <= 2 ** -7 * ref.abs().clamp(min=1.0)).all()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 24, 256, 64, 64), (1, 30, 320, 64, 128), (1, 16, 130, 128, 128), (2, 8, 640, 64, 64)])
+def test_conv_row_mode(cuda, B, H, W, Cin, Cout):
+    """Row mode (two output rows x 128 px per work item, one halo patch shared by the nine taps through row-shifted UMMA
+    views; picked automatically for Cin, Cout <= 128 and W >= 128) must agree bit for bit with the 8x16-tile kernel
+    (explicit block_n), with and without the fused max pool, and with the fp32 reference."""
+    from posecnn_b200 import conv
+    g = torch.Generator(device="cpu").manual_seed(321 + W)
+    x = torch.randn((B, H, W, Cin), generator=g).to(torch.bfloat16).to(cuda)
+    wf = (torch.randn((3, 3, Cin, Cout), generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(torch.bfloat16).to(cuda)
+    w = conv.hwio_to_tc(wf.float())
+    bias = torch.randn((Cout,), generator=g).to(cuda)
+    tile = conv.conv_bf16(x, w, bias, 3, True, Cout)       # explicit N tile -> 8x16-tile kernel
+    row = conv.conv_bf16(x, w, bias, 3, True, 0)           # automatic -> row mode
+    torch.cuda.synchronize()
+    want = ref_conv(x, wf, bias, True)
+    assert ((row.float() - want).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()
+    if Cin == 64:
+        assert torch.equal(row, tile)            # same accumulation order -> bit identical
+    else:                                        # chunk-outer vs tap-outer accumulation order: fp32 rounding only
+        assert ((row.float() - tile.float()).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()
+    rowp = conv.conv_pool_bf16(x, w, bias, 3, True, 0)
+    tilep = conv.conv_pool_bf16(x, w, bias, 3, True, Cout)
+    torch.cuda.synchronize()
+    assert torch.equal(rowp, conv.maxpool2x2(row))
+    if Cin == 64:
+        assert torch.equal(rowp, tilep)
