@@ -34,7 +34,7 @@ def hough_voting(label, vertex, extents, meta, is_train=0, threads=1):
     extents = np.ascontiguousarray(extents, np.float32); meta = np.ascontiguousarray(meta, np.float32)
     B, H, W = label.shape
     C = vertex.shape[3] // 3
-    cap = B * C * 9 + 1
+    cap = B * C * 9 * 256 + 1  # train mode keeps every hypothesis that survived the halvings (getWorkingQueue, :372-377)
     box = np.zeros((cap, 6), np.float32); pose = np.zeros((cap, 7), np.float32)
     fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
     n = lib().cpu_hough_voting(label.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), fp(vertex), fp(extents), fp(meta), B, H, W,

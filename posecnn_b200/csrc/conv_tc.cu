@@ -627,13 +627,13 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
 
 // ---------------------------------------------------------------------------------------------
 // First layer (conv1_1, Cin = 3, K = 27 -> 32) on the tensor cores with the im2col done in shared memory:
-// warps 4-7 build the A tile of an 8x16 pixel tile straight from the uint8 / f32 image (pre-processing
-// `BGR - PIXEL_MEANS` fused, zero outside the image = SAME padding) in the swizzled K-major layout, warp 8
+// warps 4-11 (two groups, alternating tiles) build the A tile of an 8x16 pixel tile straight from the uint8 / f32 image (pre-processing
+// `BGR - PIXEL_MEANS` fused, zero outside the image = SAME padding) in the swizzled K-major layout, warp 12
 // issues two K = 16 UMMAs per tile against the resident 64 x 64 weight tile, warps 0-3 run the usual
 // epilogue.  No im2col tensor ever exists in HBM.
 // ---------------------------------------------------------------------------------------------
 constexpr int kC1Stages = 6;
-constexpr int kC1Threads = 288;
+constexpr int kC1Threads = 416;  // 4 epilogue warps, 2 x 4 A-builder warps (alternating tiles), 1 MMA warp
 constexpr int kC1BarOff = kC1Stages * kABytes + 64 * 128 + 2 * kStageBytes;
 constexpr int kC1Smem = kC1BarOff + 256 + 1024;
 
@@ -656,7 +656,7 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 12 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         for (int s = 0; s < kC1Stages; s++) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
@@ -664,19 +664,22 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_holder, kTmemCols);
+    if (warp == 12) tmem_alloc(tmem_holder, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp >= 4 && warp < 8) {
-        // ===================== A builders: one tile row (pixel) per thread =====================
-        const int r = threadIdx.x - 128;
+    if (warp >= 4 && warp < 12) {
+        // ===================== A builders: one tile row (pixel) per thread; two groups take alternating tiles =====================
+        const int group = (threadIdx.x - 128) >> 7;
+        const int r = (threadIdx.x - 128) & 127;
         const int hl = r >> 4, wl = r & 15;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            if ((it & 1) != group) continue;
+            const int stage = it % kC1Stages;
+            const uint32_t phase = (it / kC1Stages) & 1;
             const int tw = tile % p.tiles_w;
             const int rest = tile / p.tiles_w;
             const int th = rest % p.tiles_h, img = rest / p.tiles_h;
@@ -714,9 +717,8 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async proxy) reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
-            if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ===================== MMA issuer (+ one-time weight load) =====================
         if (elect_one()) {
             mbar_arrive_expect_tx(wbar, 64 * 128);
@@ -793,7 +795,7 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 12) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------

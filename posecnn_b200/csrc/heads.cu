@@ -130,15 +130,19 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/,
-            const float* __restrict__ bias_v /*[3C]*/, int h, int w, int C, int* __restrict__ label /*[B,8h,8w]*/,
+            const float* __restrict__ bias_v /*[3C]*/, int h, int w, int C, int seg_cells, int* __restrict__ label /*[B,8h,8w]*/,
             float* __restrict__ vertex /*[B,8h,8w,3C]*/, float* __restrict__ prob /*[B,8h,8w,C] or null*/,
             float* __restrict__ score_out /*[B,8h,8w,C] or null*/)
 {
-    // C even: every channel pair is one 8-byte vector (vertex rows are 3C floats = 8-byte aligned)
+    // C even: every channel pair is one 8-byte vector (vertex rows are 3C floats = 8-byte aligned).
+    // A CTA produces the output pixels of `seg_cells` low-resolution cells of one output row (small shared-memory
+    // footprint -> many resident CTAs to hide the streaming-store latency).
     extern __shared__ float smem_f[];
     const int No = 4 * C, W = 8 * w, H = 8 * h, N2 = No / 2, C2 = C / 2;
-    float2* rowi = reinterpret_cast<float2*>(smem_f);   // [w][N2] vertically interpolated low-res row
-    float* sc = smem_f + (size_t)w * No;                // [W][C]  class scores of this output row
+    const int c_lo = blockIdx.z * seg_cells, c_hi = min(c_lo + seg_cells, w);   // cells [c_lo, c_hi)
+    const int s_lo = max(c_lo - 1, 0), s_hi = min(c_hi + 1, w);                 // source cells incl. halo
+    float2* rowi = reinterpret_cast<float2*>(smem_f) - (size_t)s_lo * N2;       // [s_lo, s_hi) x N2, indexed by absolute cell
+    float* sc = smem_f + (size_t)(seg_cells + 2) * No - (size_t)8 * c_lo * C;   // [8 seg_cells][C], indexed by absolute x
     const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
     // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
     const int my = y >> 3, ty = y & 7;
@@ -147,7 +151,7 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     const float wy1 = (iy1 >= 0 && iy1 < h) ? deconv_w(y - 8 * iy1 + 4, 16) : 0.f;
     const float2* r0 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy0, 0), h - 1)) * w * No);
     const float2* r1 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy1, 0), h - 1)) * w * No);
-    for (int i = t; i < w * N2; i += 256) {
+    for (int i = s_lo * N2 + t; i < s_hi * N2; i += 256) {
         const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
         rowi[i] = make_float2(fmaf(wy1, b.x, wy0 * a.x), fmaf(wy1, b.y, wy0 * a.y));
     }
@@ -163,7 +167,7 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
                                   : make_float2(bias_v[2 * c2 - C], bias_v[2 * c2 + 1 - C]);
         const bool is_score = c2 < C2;
         float* vbase = vertex + rowbase * 3 * C + 2 * (c2 - C2);
-        for (int mx = g; mx < w; mx += groups) {
+        for (int mx = c_lo + g; mx < c_hi; mx += groups) {
             const float2 zero = make_float2(0.f, 0.f);
             const float2 vl = mx > 0 ? rowi[(mx - 1) * N2 + c2] : zero;
             const float2 vc = rowi[mx * N2 + c2];
@@ -188,7 +192,7 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     }
     __syncthreads();
     // arg-max over classes, lowest index wins ties (tf.argmax); softmax for prob_normalized (network.py:474-488)
-    for (int x = t; x < W; x += 256) {
+    for (int x = 8 * c_lo + t; x < 8 * c_hi; x += 256) {
         const float* s = sc + x * C;
         float best = s[0];
         int bi = 0;
@@ -261,12 +265,14 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
     PCNN_REQUIRE(C >= 1 && B >= 1 && h >= 1 && w >= 1, "up8_heads: bad shape");
     PCNN_REQUIRE(8 * h <= 65535 * 1 && B <= 65535, "up8_heads: image too tall for the launch grid");
     PCNN_REQUIRE(C % 2 == 0 && 2 * C <= 256, "up8_heads: num_classes must be even and <= 128 (got %d)", C);
-    size_t smem = sizeof(float) * ((size_t)w * 4 * C + (size_t)8 * w * C);
-    PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: row does not fit shared memory (w = %d, C = %d)", w, C);
+    int seg_cells = w <= 20 ? w : 20;  // 160 output pixels per CTA
+    size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C);
+    PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: segment does not fit shared memory (C = %d)", C);
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_up8_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    dim3 grid(8 * h, B);
-    k_up8_heads<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, label, vertex, prob, score);
+    dim3 grid(8 * h, B, (w + seg_cells - 1) / seg_cells);
+    k_up8_heads<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, seg_cells, label, vertex, prob,
+                                                           score);
     return check_launch("up8_heads");
 }
 

@@ -192,3 +192,29 @@ def test_oracle_average_distance_properties():
         l1, _ = oracle.average_distance_loss(p2, targ, wt, pts, sym, 0.0)
         fd = (l1[0] - l0[0]) / 1e-3
         assert abs(fd - d0[n, 4 * c + k]) < 5e-3 * max(1.0, abs(fd)), (k, fd, d0[n, 4 * c + k])
+
+
+def test_cpu_hough_ransac_config0():
+    """BASELINE configs[0]: the reference's CPU hough_voting_layer (RANSAC, restated in oracle/cpu_hough_ransac.cpp) on
+    one synthetic 640x480 frame with 2 classes: planted centre within 2 px, t_z (mean LOG depth, the reference's own
+    quirk: ransac.h:105-116 has no exp) within 2 %, bit-identical across runs at 1 thread (mt19937 seed 1305)."""
+    from oracle import cpu_hough
+    sc = synth.make_scene(batch=1, height=480, width=640, num_classes=2, seed=1234 + 1000 * 0, dir_noise=0.02)
+    (b, cls, cx, cy, z), = sc["centers"]
+    box, pose = cpu_hough.hough_voting(sc["label"], sc["vertex"], sc["extents"], sc["meta"], is_train=0, threads=1)
+    assert box.shape == (1, 6) and int(box[0, 0]) == 0 and int(box[0, 1]) == 1
+    x, y = 0.5 * (box[0, 2] + box[0, 4]), 0.5 * (box[0, 3] + box[0, 5])
+    assert abs(x - cx) <= 2.0 and abs(y - cy) <= 2.0
+    assert abs(pose[0, 6] - np.log(z)) <= 0.02 * abs(np.log(z)) + 1e-3
+    np.testing.assert_allclose(pose[0, :4], [1, 0, 0, 0])
+    box2, pose2 = cpu_hough.hough_voting(sc["label"], sc["vertex"], sc["extents"], sc["meta"], is_train=0, threads=1)
+    np.testing.assert_array_equal(box, box2); np.testing.assert_array_equal(pose, pose2)
+    # nothing above minArea -> the CPU op's dummy row has cls = -1 (hough_voting_op.cc:208-222)
+    empty = np.zeros_like(sc["label"])
+    b0, p0 = cpu_hough.hough_voting(empty, sc["vertex"], sc["extents"], sc["meta"])
+    assert b0.shape == (1, 6) and b0[0, 1] == -1
+    # train mode: 9 jittered rows per detection (hough_voting_op.cc:790-855)
+    bt, pt = cpu_hough.hough_voting(sc["label"], sc["vertex"], sc["extents"], sc["meta"], is_train=1, threads=1)
+    assert bt.shape[0] % 9 == 0 and bt.shape[0] >= 9   # train mode keeps all surviving hypotheses (refSteps < 4 rule)
+    ww, hh = bt[0, 4] - bt[0, 2], bt[0, 5] - bt[0, 3]
+    np.testing.assert_allclose(bt[1:9, 4] - bt[1:9, 2], ww, rtol=1e-5); np.testing.assert_allclose(bt[1:9, 5] - bt[1:9, 3], hh, rtol=1e-5)

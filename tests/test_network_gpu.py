@@ -95,3 +95,28 @@ def test_hough_roi_pose_head_composition(net_and_out):
     x = torch.relu(x @ P["fc7/weights"] + P["fc7/biases"])
     x = torch.tanh(x @ P["fc8/weights"] + P["fc8/biases"])
     assert torch.allclose(out["poses_tanh"], x, atol=2e-2)
+
+
+def test_rgbd_two_trunk_network(cuda):
+    """input_format='RGBD' (vgg16_convs.py:99-126): second VGG trunk on the depth image, heads on the channel concat."""
+    from posecnn_b200.networks.vgg16_convs import vgg16_convs
+    net = vgg16_convs(input_format="RGBD", num_classes=4, pose_reg=False, device=cuda).init_random(seed=1, bias_std=0.05)
+    rgb, depth = synth.make_images(1, 48, 64, seed=5)
+    data = torch.from_numpy(rgb).to(cuda)
+    # depth image tiled x3 as the '_p' input (lib/fcn/test.py:70-74), already a float image
+    dp = torch.from_numpy(np.repeat((np.clip(depth / 2.0, 0, 1) * 255)[..., None], 3, -1).astype(np.float32)).to(cuda)
+    meta = torch.from_numpy(synth.make_meta(synth.intrinsics(48, 64))[None]).to(cuda)
+    ext = torch.from_numpy(synth.extents_for(4)).to(cuda)
+    out = net.forward(data, meta, ext, data_p=dp)
+    torch.cuda.synchronize()
+    P = net.params
+    x = (data.float() - torch.tensor([102.9801, 115.9465, 122.7717], device=cuda)).permute(0, 3, 1, 2)
+    f, fp = R.trunk(P, x), R.trunk(P, dp.permute(0, 3, 1, 2), "_p")
+    c4, c5 = torch.cat([f["conv4_3"], fp["conv4_3"]], 1), torch.cat([f["conv5_3"], fp["conv5_3"]], 1)
+    s5 = R.conv(c5, P["score_conv5/weights"], P["score_conv5/biases"]); s4 = R.conv(c4, P["score_conv4/weights"], P["score_conv4/biases"])
+    v4 = R.conv(f["conv4_3"], P["score_conv4_vertex/weights"], P["score_conv4_vertex/biases"], False)
+    v5 = R.conv(f["conv5_3"], P["score_conv5_vertex/weights"], P["score_conv5_vertex/biases"], False)
+    score, label, prob, vertex = R.heads_from_scores(P, s4, s5, v4, v5)
+    assert rel_l2(out["vertex_pred"].permute(0, 3, 1, 2), vertex) < 2e-2
+    got_s4 = out["score_conv4"].float().permute(0, 3, 1, 2)
+    assert rel_l2(got_s4, s4) < 2e-2
