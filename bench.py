@@ -268,27 +268,48 @@ def run_full(args, rank, world, local):
         hs.append(e0.elapsed_time(e1))
     hough_ms = float(np.median(hs))
 
-    # end to end through the public API with HOST buffers: pinned uint8 images in, ROI / pose records out
+    # end to end through the public API with HOST buffers: every step uploads its own pinned uint8 batch (H2D) and
+    # reads its pose records back (D2H), all inside the timed region.  The upload of step i+1 runs on a copy stream
+    # while step i computes (double-buffered device input), as a serving loop would do.
     e2e = None
     if not args.no_e2e:
-        h_rec = torch.empty((rec.shape[0], rec.shape[1]), dtype=torch.float32).pin_memory()
-        d_in = torch.empty_like(d_img)
+        h_rec = [torch.empty((rec.shape[0], rec.shape[1]), dtype=torch.float32).pin_memory() for _ in range(2)]
+        d_in = [torch.empty_like(d_img) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        up_done = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        main = torch.cuda.current_stream()
 
-        def e2e_step():
-            d_in.copy_(h_img, non_blocking=True)
-            r, _ = step(d_in)
-            h_rec.copy_(r, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        def upload(i):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])       # the step that last read this buffer has finished with it
+                d_in[b].copy_(h_img, non_blocking=True)
+                up_done[b].record(copy_stream)
 
-        e2e_step()
+        def run_e2e(k):
+            for b in range(2):
+                consumed[b].record(main)
+            upload(0)
+            for i in range(k):
+                b = i & 1
+                if i + 1 < k:
+                    upload(i + 1)
+                main.wait_event(up_done[b])
+                r, _ = step(d_in[b])
+                consumed[b].record(main)
+                h_rec[b].copy_(r, non_blocking=True)
+            main.synchronize()
+
+        run_e2e(2)
         barrier(world)
+        k = max(4, min(args.steps, 20))
         t0 = time.perf_counter()
-        k = max(2, min(args.steps, 10))
-        for _ in range(k):
-            e2e_step()
+        run_e2e(k)
         dt = max_over_ranks((time.perf_counter() - t0) / k, world)
         e2e = dict(value=B * world / dt, unit="frames/s", h2d_bytes_per_step=int(h_img.numel()),
-                   d2h_bytes_per_step=int(h_rec.numel() * 4))
+                   d2h_bytes_per_step=int(h_rec[0].numel() * 4), note="pinned host uint8 images -> pose records on the host; upload of "
+                   "step i+1 overlapped with the compute of step i on a copy stream; wall clock over %d steps" % k)
     peaks = measured_peaks()
     tf = VGG_FLOP_PER_FRAME * B / (trunk_ms * 1e-3) / 1e12
     peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]

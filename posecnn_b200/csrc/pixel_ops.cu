@@ -126,6 +126,7 @@ k_roi_pool_fwd_bf16(const __nv_bfloat16* __restrict__ bottom, const float* __res
         if (!empty) {
             const __nv_bfloat16* img = bottom + (size_t)rb.b * height * width * channels;
             for (int h = rb.hs; h < rb.he; h++)
+#pragma unroll 4
                 for (int w = rb.ws; w < rb.we; w++) {
                     int bi = (h * width + w) * channels + g * 8;
                     uint4 q = __ldg(reinterpret_cast<const uint4*>(img + bi));
@@ -340,14 +341,15 @@ __global__ void __launch_bounds__(256)
 k_pixel_gather(const float* __restrict__ vox, const float* __restrict__ depth, const float* __restrict__ meta, int B,
                int H, int W, int Cf, int num_meta, int G, float* __restrict__ out)
 {
-    const int cg = Cf / VEC;
-    const size_t total = (size_t)B * H * W * cg;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        int g = (int)(idx % cg);
-        size_t pix = idx / cg;
-        int w = (int)(pix % W);
-        int h = (int)((pix / W) % H);
-        int n = (int)(pix / ((size_t)W * H));
+    // grid.y = image; 32-bit index math inside the image (64-bit div/mod costs ~100 instructions each)
+    const unsigned cg = Cf / VEC;
+    const unsigned total = (unsigned)H * W * cg;
+    const int n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const unsigned pl = i / cg;
+        const int w = (int)(pl % W), h = (int)(pl / W);
+        const size_t pix = (size_t)n * H * W + pl;
         int vd, vh, vw;
         bool inside = pixel_to_voxel(meta + (size_t)n * num_meta, w, h, __ldg(depth + pix), G, vd, vh, vw);
         if (VEC == 4) {
@@ -369,15 +371,15 @@ k_voxel_average(const float* __restrict__ src, const float* __restrict__ depth, 
                 const float* __restrict__ fallback, int B, int H, int W, int nch, int num_meta, int G, int ks,
                 float threshold, float* __restrict__ dst, float* __restrict__ flag)
 {
-    const int cg = nch / VEC;
-    const size_t total = (size_t)B * G * G * G * cg;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        int g = (int)(idx % cg);
-        size_t vox = idx / cg;
-        int w = (int)(vox % G);
-        int h = (int)((vox / G) % G);
-        int d = (int)((vox / ((size_t)G * G)) % G);
-        int n = (int)(vox / ((size_t)G * G * G));
+    // grid.y = image; 32-bit index math inside the image
+    const unsigned cg = nch / VEC;
+    const unsigned total = (unsigned)G * G * G * cg;
+    const int n = blockIdx.y;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const unsigned vl = i / cg;
+        const int w = (int)(vl % G), h = (int)((vl / G) % G), d = (int)(vl / ((unsigned)G * G));
+        const size_t vox = (size_t)n * G * G * G + vl;
         int px, py;
         float Z1;
         voxel_to_pixel(meta + (size_t)n * num_meta, d, h, w, px, py, Z1);
@@ -423,6 +425,82 @@ k_voxel_average(const float* __restrict__ src, const float* __restrict__ depth, 
         } else {
             dst[vox * nch + g] = acc[0];
             if (flag) flag[vox * nch + g] = fl;
+        }
+    }
+}
+
+// Wide-thread forms of the window average: every thread of k_voxel_average repeats the (2k+1)^2 depth tests of its
+// voxel, so fewer threads per voxel = fewer redundant tests.  CPT channels per thread, kept in registers:
+//   CPT = 16 (nch % 16 == 0): four 128-bit loads per hit, four streaming stores;
+//   CPT = 32 (nch <= 32, e.g. the C = 22 label channels): one thread owns the whole voxel.
+template <int CPT, bool WHOLE>
+__global__ void __launch_bounds__(256)
+k_voxel_average_wide(const float* __restrict__ src, const float* __restrict__ depth, const float* __restrict__ meta,
+                     const float* __restrict__ fallback, int H, int W, int nch, int num_meta, int G, int ks,
+                     float threshold, float* __restrict__ dst, float* __restrict__ flag)
+{
+    const unsigned cg = WHOLE ? 1u : (unsigned)nch / CPT;
+    const unsigned total = (unsigned)G * G * G * cg;
+    const int n = blockIdx.y;
+    const int nc = WHOLE ? nch : CPT;  // channels handled by this thread
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const unsigned vl = i / cg;
+        const int w = (int)(vl % G), h = (int)((vl / G) % G), d = (int)(vl / ((unsigned)G * G));
+        const size_t vox = (size_t)n * G * G * G + vl;
+        int px, py;
+        float Z1;
+        voxel_to_pixel(meta + (size_t)n * num_meta, d, h, w, px, py, Z1);
+        float acc[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; k++) acc[k] = 0.f;
+        int count = 0;
+        const int x0 = max(px - ks, 0), x1 = min(px + ks, W - 1);
+        const int y0 = max(py - ks, 0), y1 = min(py + ks, H - 1);
+        for (int x = x0; x <= x1; x++)
+            for (int y = y0; y <= y1; y++) {
+                const size_t pix = ((size_t)n * H + y) * W + x;
+                if (fabsf(__fsub_rn(__ldg(depth + pix), Z1)) < threshold) {
+                    count++;
+                    const float* sp = src + pix * nch + g * CPT;
+                    if (!WHOLE) {
+#pragma unroll
+                        for (int k = 0; k < CPT; k += 4) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(sp + k));
+                            acc[k] += q.x; acc[k + 1] += q.y; acc[k + 2] += q.z; acc[k + 3] += q.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CPT; k++)
+                            if (k < nc) acc[k] += __ldg(sp + k);
+                    }
+                }
+            }
+        float fl = 0.f;
+        if (count == 0) {
+            if (fallback) {
+                const float* fp = fallback + vox * nch + g * CPT;
+#pragma unroll
+                for (int k = 0; k < CPT; k++)
+                    if (k < nc) acc[k] = __ldg(fp + k);
+            }
+        } else {
+            const float cf = (float)count;
+#pragma unroll
+            for (int k = 0; k < CPT; k++) acc[k] = __fdiv_rn(acc[k], cf);
+            fl = 1.f;
+        }
+        float* dp = dst + vox * nch + g * CPT;
+        if (!WHOLE) {
+#pragma unroll
+            for (int k = 0; k < CPT; k += 4) {
+                st_stream_f4(reinterpret_cast<float4*>(dp + k), make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]));
+                if (flag) st_stream_f4(reinterpret_cast<float4*>(flag + vox * nch + g * CPT + k), make_float4(fl, fl, fl, fl));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPT; k++)
+                if (k < nc) { dp[k] = acc[k]; if (flag) flag[vox * nch + k] = fl; }
         }
     }
 }
@@ -516,12 +594,13 @@ extern "C" int pcnn_hard_label_bwd(int B, int H, int W, int C, float* grad_prob,
 static int launch_gather(const float* vox, const float* depth, const float* meta, int B, int H, int W, int Cf,
                          int num_meta, int G, float* out, cudaStream_t st)
 {
+    if ((size_t)H * W * Cf >= 0x7fffffffULL || B > 65535) { set_error("project: image too large for 32-bit indexing"); return PCNN_E_INVALID; }
     if (Cf % 4 == 0 && aligned16(vox) && aligned16(out)) {
-        size_t total = (size_t)B * H * W * (Cf / 4);
-        k_pixel_gather<4><<<grid_for(total, 256), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
+        size_t total = (size_t)H * W * (Cf / 4);
+        k_pixel_gather<4><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
     } else {
-        size_t total = (size_t)B * H * W * Cf;
-        k_pixel_gather<1><<<grid_for(total, 256), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
+        size_t total = (size_t)H * W * Cf;
+        k_pixel_gather<1><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(vox, depth, meta, B, H, W, Cf, num_meta, G, out);
     }
     return check_launch("pixel gather");
 }
@@ -531,14 +610,27 @@ static int launch_average(const float* src, const float* depth, const float* met
 {
     bool v4 = nch % 4 == 0 && aligned16(src) && aligned16(dst) && (!fallback || aligned16(fallback)) &&
               (!flag || aligned16(flag));
+    if ((size_t)G * G * G * nch >= 0x7fffffffULL || B > 65535) { set_error("backproject: grid too large for 32-bit indexing"); return PCNN_E_INVALID; }
+    if (v4 && nch % 16 == 0) {
+        size_t total = (size_t)G * G * G * (nch / 16);
+        k_voxel_average_wide<16, false><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(src, depth, meta, fallback, H, W, nch, num_meta,
+                                                                                         G, ks, thr, dst, flag);
+        return check_launch("voxel average (16 channels / thread)");
+    }
+    if (!v4 && nch <= 32) {
+        size_t total = (size_t)G * G * G;
+        k_voxel_average_wide<32, true><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(src, depth, meta, fallback, H, W, nch, num_meta,
+                                                                                        G, ks, thr, dst, flag);
+        return check_launch("voxel average (whole voxel / thread)");
+    }
     if (v4) {
-        size_t total = (size_t)B * G * G * G * (nch / 4);
-        k_voxel_average<4><<<grid_for(total, 256), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G, ks,
-                                                                 thr, dst, flag);
+        size_t total = (size_t)G * G * G * (nch / 4);
+        k_voxel_average<4><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G,
+                                                                             ks, thr, dst, flag);
     } else {
-        size_t total = (size_t)B * G * G * G * nch;
-        k_voxel_average<1><<<grid_for(total, 256), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G, ks,
-                                                                 thr, dst, flag);
+        size_t total = (size_t)G * G * G * nch;
+        k_voxel_average<1><<<dim3(grid_for(total, 256, 8), B), 256, 0, st>>>(src, depth, meta, fallback, B, H, W, nch, num_meta, G,
+                                                                             ks, thr, dst, flag);
     }
     return check_launch("voxel average");
 }
