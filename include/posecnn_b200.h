@@ -179,6 +179,9 @@ int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int 
  * and (optional) prob_normalized / score [B,H,W,C] f32.
  *   score4/vert4 [B,h,w,Cs|Cv] bf16 (1x1 convs of conv4_3), score5/vert5 [B,h/2,w/2,Cs|Cv] bf16,
  *   w_score [Cs][C] f32, w_vertex [Cv][3C] f32, lowres [B,h,w,4C] f32, H = 8h, W = 8w.
+ *   w_vertex == NULL: "folded" vertex head -- the caller multiplied the vertex_pred matrix into the two vertex 1x1
+ *   convolutions (linear, no ReLU between them: vgg16_convs.py:151-163), vert4 / vert5 then hold the 3C vertex
+ *   channels directly (row stride Cv >= 3C, zero padded) and the kernel only adds and up-samples them.
  */
 int pcnn_lowres_heads(const void* score4, const void* score5, const void* vert4, const void* vert5,
                       const float* w_score, const float* w_vertex, int B, int h, int w, int Cs, int Cv, int C,

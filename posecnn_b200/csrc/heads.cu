@@ -38,12 +38,19 @@ __host__ __device__ inline float deconv_w(int x, int k)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_lowres_heads: one warp per pair of low-resolution pixels.  Lanes first build the two "add" vectors
-// (conv4 branch + 4x4/2 transposed convolution of the conv5 branch, coalesced bf16 reads) in the warp's
-// shared-memory slot, then every lane owns up to three of the 4C outputs and runs the two small matrix
-// products out of shared memory (weights conflict-free over lanes, activations broadcast).
+// k_lowres_heads: one warp per group of 8 consecutive low-resolution pixels.
+//   phase 1  lane (q = lane & 7, g = lane >> 3) builds pixel q's two "add" vectors (conv4 branch + 4x4/2
+//            transposed convolution of the conv5 branch; 8-byte bf16x4 reads) into the warp's shared-memory
+//            slot, channel-major: sx[ch][8 pixels].
+//   phase 2  register-tiled matrix products: every lane owns one output column for all 8 pixels, so one k step
+//            costs 1 weight word + 2 broadcast float4 of activations for 8 FMAs.  The 4C outputs are covered in
+//            three passes of <= 32 columns: vertex 0..31, vertex 32..63 (K = Cv), then the C score columns
+//            (K = Cs) next to the remaining vertex columns, each of those split over Cv/Cs lanes of Cs rows and
+//            summed by shuffle, so no lane idles behind a longer loop.
+// Requires Cs % 4 == 0, Cv % Cs == 0 (64 / 128 in the network).
 // ---------------------------------------------------------------------------------------------
 constexpr int kLrWarps = 8;
+constexpr int kLrPix = 8;
 
 __global__ void __launch_bounds__(256)
 k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_bfloat16* __restrict__ s5 /*[B,h/2,w/2,Cs]*/,
@@ -51,94 +58,193 @@ k_lowres_heads(const __nv_bfloat16* __restrict__ s4 /*[B,h,w,Cs]*/, const __nv_b
                const float* __restrict__ Ws /*[Cs][C]*/, const float* __restrict__ Wv /*[Cv][3C]*/, int B, int h, int w,
                int Cs, int Cv, int C, float* __restrict__ out /*[B,h,w,4C]*/)
 {
-    extern __shared__ float sm[];
-    const int Ct = Cs + Cv;        // channels of the two "add" tensors
+    extern __shared__ __align__(16) float sm[];
+    // folded mode (Wv == NULL): the vertex_pred matrix was multiplied into the two vertex 1x1 convolutions on the host
+    // (both are linear, no ReLU between them), so v4 / v5 already hold the 3C vertex channels (row stride Cv) and the
+    // vertex outputs are just v4 + up2(v5)
+    const bool folded = Wv == nullptr;
+    const int Ct = folded ? Cs : Cs + Cv;   // channels staged in shared memory
     const int No = 4 * C;          // outputs per pixel
-    float* sW = sm;                // [Cs*C + Cv*3C]
-    float* sx_all = sm + Cs * C + Cv * 3 * C;  // [kLrWarps][2][Ct]
+    const int C3 = folded ? 0 : 3 * C;      // vertex columns of the matrix phase
+    float* sx_all = sm;                               // [kLrWarps][Ct][8]   (16-byte aligned rows)
+    float* sW = sm + kLrWarps * Ct * kLrPix;          // [Cs*C + Cv*3C]
     for (int i = threadIdx.x; i < Cs * C; i += blockDim.x) sW[i] = Ws[i];
-    for (int i = threadIdx.x; i < Cv * 3 * C; i += blockDim.x) sW[Cs * C + i] = Wv[i];
+    if (!folded)
+        for (int i = threadIdx.x; i < Cv * C3; i += blockDim.x) sW[Cs * C + i] = Wv[i];
     __syncthreads();
+    const float* sWv = sW + Cs * C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* sx = sx_all + warp * 2 * Ct;
+    float* sx = sx_all + warp * Ct * kLrPix;
     const int npix = B * h * w;
     const int h5 = h / 2, w5 = w / 2;
-    const int npairs = (npix + 1) / 2;
-    for (int pr = blockIdx.x * kLrWarps + warp; pr < npairs; pr += gridDim.x * kLrWarps) {
-        // ---- add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int p = 2 * pr + q;
-            if (p >= npix) { for (int ch = lane; ch < Ct; ch += 32) sx[q * Ct + ch] = 0.f; continue; }
-            const int x = p % w, y = (p / w) % h, n = p / (w * h);
+    const int ngroups = (npix + kLrPix - 1) / kLrPix;
+    const int q = lane & 7, g = lane >> 3;
+    const int nquads = Ct / 4;
+    // column map: n_full passes of 32 vertex columns (K = Cv); then "tail" passes whose lane jobs are the C score
+    // columns (K = Cs) followed, from a split-aligned start, by split = Cv / Cs partial lanes per left-over vertex column
+    const int split = Cv / Cs;
+    const int n_full = C3 / 32, v_left = C3 - 32 * n_full;
+    const int tail_start = (C + split - 1) / split * split;
+    const int n_pass = n_full + (tail_start + v_left * split + 31) / 32;
+    for (int grp = blockIdx.x * kLrWarps + warp; grp < ngroups; grp += gridDim.x * kLrWarps) {
+        // ---- phase 1: add = conv4 branch + up2(conv5 branch): conv2d_transpose 4x4 / stride 2, SAME (pad 1)
+        {
+            const int p = grp * kLrPix + q;
+            const bool live = p < npix;
+            const int pc = live ? p : npix - 1;
+            const int x = pc % w, y = (pc / w) % h, n = pc / (w * h);
             // out[o] += in[i] * W[o - 2 i + 1], 0 <= o - 2i + 1 <= 3: two source rows / columns
             const int iy0 = ((y + 1) >> 1) - 1, ix0 = ((x + 1) >> 1) - 1;
             float wgt[4];
-            size_t off5[4];
+            int off5[4];
 #pragma unroll
             for (int d = 0; d < 4; d++) {
                 const int iy = iy0 + (d >> 1), ix = ix0 + (d & 1);
                 const int ky = y - 2 * iy + 1, kx = x - 2 * ix + 1;
                 const bool ok = iy >= 0 && iy < h5 && ix >= 0 && ix < w5;
                 wgt[d] = ok ? deconv_w(ky, 4) * deconv_w(kx, 4) : 0.f;
-                off5[d] = ((size_t)(n * h5 + min(max(iy, 0), h5 - 1)) * w5 + min(max(ix, 0), w5 - 1));
+                off5[d] = (n * h5 + min(max(iy, 0), h5 - 1)) * w5 + min(max(ix, 0), w5 - 1);
             }
-            for (int ch = lane; ch < Ct; ch += 32) {
+            for (int qd = g; qd < nquads; qd += 4) {
+                const int ch = 4 * qd;
                 const bool vert = ch >= Cs;
                 const int cc = vert ? ch - Cs : ch, Cn = vert ? Cv : Cs;
                 const __nv_bfloat16* a = vert ? v4 : s4;
                 const __nv_bfloat16* b5 = vert ? v5 : s5;
-                float up = wgt[0] * __bfloat162float(b5[off5[0] * Cn + cc]);
-                up = fmaf(wgt[1], __bfloat162float(b5[off5[1] * Cn + cc]), up);
-                up = fmaf(wgt[2], __bfloat162float(b5[off5[2] * Cn + cc]), up);
-                up = fmaf(wgt[3], __bfloat162float(b5[off5[3] * Cn + cc]), up);
-                sx[q * Ct + ch] = __bfloat162float(a[(size_t)p * Cn + cc]) + up;
+                const uint2 ua = __ldg(reinterpret_cast<const uint2*>(a + (size_t)pc * Cn + cc));
+                float acc[4];
+                {
+                    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&ua.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&ua.y);
+                    acc[0] = __low2float(lo); acc[1] = __high2float(lo); acc[2] = __low2float(hi); acc[3] = __high2float(hi);
+                }
+                float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int d = 0; d < 4; d++) {
+                    const uint2 ub = __ldg(reinterpret_cast<const uint2*>(b5 + (size_t)off5[d] * Cn + cc));
+                    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&ub.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&ub.y);
+                    if (d == 0) {
+                        up[0] = wgt[0] * __low2float(lo); up[1] = wgt[0] * __high2float(lo);
+                        up[2] = wgt[0] * __low2float(hi); up[3] = wgt[0] * __high2float(hi);
+                    } else {
+                        up[0] = fmaf(wgt[d], __low2float(lo), up[0]); up[1] = fmaf(wgt[d], __high2float(lo), up[1]);
+                        up[2] = fmaf(wgt[d], __low2float(hi), up[2]); up[3] = fmaf(wgt[d], __high2float(hi), up[3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) sx[(ch + i) * kLrPix + q] = live ? acc[i] + up[i] : 0.f;
+            }
+            if (folded && live) {
+                // vertex outputs straight to HBM: channels [4 qd, 4 qd + 4) of the 3C (tensor rows are zero padded to Cv)
+                float* op = out + (size_t)p * No + C;
+                const int nvq = (3 * C + 3) / 4;
+                for (int qd = g; qd < nvq; qd += 4) {
+                    const int cc = 4 * qd;
+                    const uint2 ua = __ldg(reinterpret_cast<const uint2*>(v4 + (size_t)pc * Cv + cc));
+                    const __nv_bfloat162 alo = *reinterpret_cast<const __nv_bfloat162*>(&ua.x), ahi = *reinterpret_cast<const __nv_bfloat162*>(&ua.y);
+                    float r[4] = {__low2float(alo), __high2float(alo), __low2float(ahi), __high2float(ahi)};
+                    float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int d = 0; d < 4; d++) {
+                        const uint2 ub = __ldg(reinterpret_cast<const uint2*>(v5 + (size_t)off5[d] * Cv + cc));
+                        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&ub.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&ub.y);
+                        if (d == 0) {
+                            up[0] = wgt[0] * __low2float(lo); up[1] = wgt[0] * __high2float(lo);
+                            up[2] = wgt[0] * __low2float(hi); up[3] = wgt[0] * __high2float(hi);
+                        } else {
+                            up[0] = fmaf(wgt[d], __low2float(lo), up[0]); up[1] = fmaf(wgt[d], __high2float(lo), up[1]);
+                            up[2] = fmaf(wgt[d], __low2float(hi), up[2]); up[3] = fmaf(wgt[d], __high2float(hi), up[3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (cc + i < 3 * C) op[cc + i] = r[i] + up[i];
+                }
             }
         }
         __syncwarp();
-        // ---- outputs o = lane, lane + 32, lane + 64, ... for both pixels
-        for (int o = lane; o < No; o += 32) {
-            float a0 = 0.f, a1 = 0.f;
-            if (o < C) {
-                const float* wp = sW + o;
-                for (int k = 0; k < Cs; k++) {
-                    const float wk = wp[k * C];
-                    a0 = fmaf(sx[k], wk, a0);
-                    a1 = fmaf(sx[Ct + k], wk, a1);
-                }
+        // ---- phase 2
+        const int p0 = grp * kLrPix;
+        const int nlive = min(kLrPix, npix - p0);
+        float* obase = out + (size_t)p0 * No;
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; pass++) {
+            // column / K-range of this lane in this pass
+            const float* wp;      // weight of (k = 0) for this lane's column, stride ld
+            const float* xp;      // activations of (k = 0)
+            int ld, kn, col;      // col = output index within the 4C outputs, or -1 (idle)
+            bool partial = false; // tail vertex lanes hold a partial sum
+            if (pass < n_full) {
+                const int vc = 32 * pass + lane;
+                col = C + vc; wp = sWv + vc; ld = C3; kn = Cv; xp = sx + Cs * kLrPix;
             } else {
-                const float* wp = sW + Cs * C + (o - C);
-                const int ld = 3 * C;
-                for (int k = 0; k < Cv; k++) {
-                    const float wk = wp[k * ld];
-                    a0 = fmaf(sx[Cs + k], wk, a0);
-                    a1 = fmaf(sx[Ct + Cs + k], wk, a1);
+                const int job = 32 * (pass - n_full) + lane;
+                kn = Cs;
+                if (job < C) {
+                    col = job; wp = sW + job; ld = C; xp = sx;
+                } else {
+                    const int j = job - tail_start;
+                    const bool ok = j >= 0 && j < v_left * split;
+                    const int vc = ok ? 32 * n_full + j / split : 0, part = ok ? j % split : 0;
+                    col = ok ? C + vc : -1; partial = ok;
+                    wp = ok ? sWv + (size_t)(part * Cs) * C3 + vc : sW; ld = ok ? C3 : 0;   // idle lanes re-read one valid word
+                    xp = ok ? sx + (Cs + part * Cs) * kLrPix : sx;
                 }
             }
-            const int p0 = 2 * pr;
-            out[(size_t)p0 * No + o] = a0;
-            if (p0 + 1 < npix) out[(size_t)(p0 + 1) * No + o] = a1;
+            float acc[kLrPix];
+#pragma unroll
+            for (int i = 0; i < kLrPix; i++) acc[i] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < kn; k++) {
+                const float wk = wp[k * ld];
+                const float4 x0 = *reinterpret_cast<const float4*>(xp + k * kLrPix);
+                const float4 x1 = *reinterpret_cast<const float4*>(xp + k * kLrPix + 4);
+                acc[0] = fmaf(x0.x, wk, acc[0]); acc[1] = fmaf(x0.y, wk, acc[1]);
+                acc[2] = fmaf(x0.z, wk, acc[2]); acc[3] = fmaf(x0.w, wk, acc[3]);
+                acc[4] = fmaf(x1.x, wk, acc[4]); acc[5] = fmaf(x1.y, wk, acc[5]);
+                acc[6] = fmaf(x1.z, wk, acc[6]); acc[7] = fmaf(x1.w, wk, acc[7]);
+            }
+            if (pass >= n_full && split > 1) {
+                // sum the `split` adjacent partial lanes of a left-over vertex column (split is a power of two)
+                for (int d = 1; d < split; d <<= 1) {
+#pragma unroll
+                    for (int i = 0; i < kLrPix; i++) {
+                        const float o = __shfl_down_sync(0xffffffffu, acc[i], d);
+                        if (partial) acc[i] += o;
+                    }
+                }
+                if (partial && ((32 * (pass - n_full) + lane - tail_start) % split) != 0) col = -1;
+            }
+            if (col >= 0) {
+#pragma unroll
+                for (int i = 0; i < kLrPix; i++)
+                    if (i < nlive) obase[(size_t)i * No + col] = acc[i];
+            }
         }
         __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_up8_heads: one CTA per output row (y, image).  The two contributing low-resolution rows are
-// combined vertically into shared memory once; every output value is then a 2-tap horizontal blend.
-// Class scores of the row are kept in shared memory for the per-pixel arg-max / softmax.
+// k_up8_heads: one CTA per (output row, image, segment of low-resolution cells).  The two contributing
+// low-resolution rows are combined vertically into shared memory once; every output value is then a 2-tap horizontal
+// blend with compile-time weights.  Class scores of the segment are kept in shared memory for the per-pixel arg-max /
+// softmax.  CT = compile-time class count (0 = run-time): with CT fixed every store address of a thread is
+// `base + immediate`, which is what takes this kernel from instruction-bound to store-bound (ncu: 1.29 G warp
+// instructions, 24 % of them IMAD address math, before the change).
+// Thread roles: threads [0, nv) own one vertex channel pair of one cell phase (consecutive lanes = consecutive channel
+// pairs -> contiguous 8-byte stores), threads [nv, nv + ns) own one score channel pair.
 // ---------------------------------------------------------------------------------------------
+template <int CT>
 __global__ void __launch_bounds__(256)
 k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/,
-            const float* __restrict__ bias_v /*[3C]*/, int h, int w, int C, int seg_cells, int* __restrict__ label /*[B,8h,8w]*/,
+            const float* __restrict__ bias_v /*[3C]*/, int h, int w, int C_rt, int seg_cells, int* __restrict__ label /*[B,8h,8w]*/,
             float* __restrict__ vertex /*[B,8h,8w,3C]*/, float* __restrict__ prob /*[B,8h,8w,C] or null*/,
             float* __restrict__ score_out /*[B,8h,8w,C] or null*/)
 {
     // C even: every channel pair is one 8-byte vector (vertex rows are 3C floats = 8-byte aligned).
-    // A CTA produces the output pixels of `seg_cells` low-resolution cells of one output row (small shared-memory
-    // footprint -> many resident CTAs to hide the streaming-store latency).
     extern __shared__ float smem_f[];
-    const int No = 4 * C, W = 8 * w, H = 8 * h, N2 = No / 2, C2 = C / 2;
+    const int C = CT ? CT : C_rt;
+    const int No = 4 * C, W = 8 * w, H = 8 * h, N2 = No / 2, C2 = C / 2, V2 = 3 * C2;
     const int c_lo = blockIdx.z * seg_cells, c_hi = min(c_lo + seg_cells, w);   // cells [c_lo, c_hi)
     const int s_lo = max(c_lo - 1, 0), s_hi = min(c_hi + 1, w);                 // source cells incl. halo
     float2* rowi = reinterpret_cast<float2*>(smem_f) - (size_t)s_lo * N2;       // [s_lo, s_hi) x N2, indexed by absolute cell
@@ -157,49 +263,75 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     }
     __syncthreads();
     const size_t rowbase = ((size_t)n * H + y) * W;
-    // thread = (cell phase g, channel pair c2): a fixed channel pair, strided over the low-resolution cells of the
-    // row; the 8 output pixels of a cell blend the same three source values with compile-time weights.  Consecutive
-    // lanes hold consecutive channel pairs, so the vertex stores of a pixel are contiguous.
-    const int groups = 256 / N2;
-    const int g = t / N2, c2 = t - g * N2;
-    if (g < groups) {
-        const float2 bb = c2 < C2 ? make_float2(bias_s[2 * c2], bias_s[2 * c2 + 1])
-                                  : make_float2(bias_v[2 * c2 - C], bias_v[2 * c2 + 1 - C]);
-        const bool is_score = c2 < C2;
-        float* vbase = vertex + rowbase * 3 * C + 2 * (c2 - C2);
-        for (int mx = c_lo + g; mx < c_hi; mx += groups) {
-            const float2 zero = make_float2(0.f, 0.f);
-            const float2 vl = mx > 0 ? rowi[(mx - 1) * N2 + c2] : zero;
-            const float2 vc = rowi[mx * N2 + c2];
-            const float2 vr = mx + 1 < w ? rowi[(mx + 1) * N2 + c2] : zero;
+    const float2 zero = make_float2(0.f, 0.f);
+    // x = 8 mx + tx: sources (mx-1, mx) with taps (tx+12, tx+4) for tx < 4, (mx, mx+1) with (tx+4, tx-4) otherwise
+#define PCNN_UP8_BLEND(tx, v0, v1)                                                                             \
+    const float wa = deconv_w(tx < 4 ? tx + 12 : tx + 4, 16), wb = deconv_w(tx < 4 ? tx + 4 : tx - 4, 16);     \
+    const float2 a = tx < 4 ? vl : vc, b = tx < 4 ? vc : vr;                                                   \
+    float v0 = fmaf(wb, b.x, wa * a.x) + bb.x;                                                                 \
+    float v1 = fmaf(wb, b.y, wa * a.y) + bb.y;
+    const int gv = 256 / N2;                 // cell phases; vertex threads [0, gv*V2), score threads [gv*V2, gv*N2)
+    const int nv = gv * V2;
+    if (t < nv) {
+        const int g = t / V2, c2 = t - g * V2;                   // vertex channel pair c2 (channels C + 2 c2, +1 of a lowres cell)
+        const float2 bb = make_float2(bias_v[2 * c2], bias_v[2 * c2 + 1]);
+        const float2* src = rowi + C2 + c2;
+        float* vp = vertex + (rowbase + 8 * (size_t)(c_lo + g)) * 3 * C + 2 * c2;
+        const int vstep = gv * 8 * 3 * C;
+        for (int mx = c_lo + g; mx < c_hi; mx += gv, vp += vstep) {
+            const float2 vl = mx > 0 ? src[(mx - 1) * N2] : zero;
+            const float2 vc = src[mx * N2];
+            const float2 vr = mx + 1 < w ? src[(mx + 1) * N2] : zero;
 #pragma unroll
             for (int tx = 0; tx < 8; tx++) {
-                // x = 8 mx + tx: sources (mx-1, mx) with taps (tx+12, tx+4) for tx < 4, (mx, mx+1) with (tx+4, tx-4) otherwise
-                const float wa = deconv_w(tx < 4 ? tx + 12 : tx + 4, 16), wb = deconv_w(tx < 4 ? tx + 4 : tx - 4, 16);
-                const float2 a = tx < 4 ? vl : vc, b = tx < 4 ? vc : vr;
-                float v0 = fmaf(wb, b.x, wa * a.x) + bb.x;
-                float v1 = fmaf(wb, b.y, wa * a.y) + bb.y;
-                const int x = 8 * mx + tx;
-                if (is_score) {
-                    v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);  // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
-                    *reinterpret_cast<float2*>(sc + x * C + 2 * c2) = make_float2(v0, v1);
-                    if (score_out) *reinterpret_cast<float2*>(score_out + (rowbase + x) * C + 2 * c2) = make_float2(v0, v1);
-                } else {
-                    *reinterpret_cast<float2*>(vbase + (size_t)x * 3 * C) = make_float2(v0, v1);
-                }
+                PCNN_UP8_BLEND(tx, v0, v1)
+                __stcs(reinterpret_cast<float2*>(vp + tx * 3 * C), make_float2(v0, v1));
             }
         }
+    } else if (t < gv * N2) {
+        const int u = t - nv;
+        const int g = u / C2, c2 = u - g * C2;                   // score channel pair
+        const float2 bb = make_float2(bias_s[2 * c2], bias_s[2 * c2 + 1]);
+        const float2* src = rowi + c2;
+        float* sp = sc + 8 * (c_lo + g) * C + 2 * c2;
+        float* gp = score_out ? score_out + (rowbase + 8 * (size_t)(c_lo + g)) * C + 2 * c2 : nullptr;
+        for (int mx = c_lo + g; mx < c_hi; mx += gv, sp += gv * 8 * C) {
+            const float2 vl = mx > 0 ? src[(mx - 1) * N2] : zero;
+            const float2 vc = src[mx * N2];
+            const float2 vr = mx + 1 < w ? src[(mx + 1) * N2] : zero;
+#pragma unroll
+            for (int tx = 0; tx < 8; tx++) {
+                PCNN_UP8_BLEND(tx, v0, v1)
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);        // `score` has a ReLU (vgg16_convs.py:141, network.py:160)
+                *reinterpret_cast<float2*>(sp + tx * C) = make_float2(v0, v1);
+                if (gp) *reinterpret_cast<float2*>(gp + tx * C) = make_float2(v0, v1);
+            }
+            if (gp) gp += gv * 8 * C;
+        }
     }
+#undef PCNN_UP8_BLEND
     __syncthreads();
     // arg-max over classes, lowest index wins ties (tf.argmax); softmax for prob_normalized (network.py:474-488)
     for (int x = 8 * c_lo + t; x < 8 * c_hi; x += 256) {
-        const float* s = sc + x * C;
-        float best = s[0];
+        const float2* s2 = reinterpret_cast<const float2*>(sc + x * C);
+        float best = s2[0].x;
         int bi = 0;
-        for (int c = 1; c < C; c++)
-            if (s[c] > best) { best = s[c]; bi = c; }
+        if (s2[0].y > best) { best = s2[0].y; bi = 1; }
+#pragma unroll
+        for (int c = 1; c < (CT ? CT / 2 : 1); c++) {
+            const float2 v = s2[c];
+            if (v.x > best) { best = v.x; bi = 2 * c; }
+            if (v.y > best) { best = v.y; bi = 2 * c + 1; }
+        }
+        if (!CT)
+            for (int c = 1; c < C2; c++) {
+                const float2 v = s2[c];
+                if (v.x > best) { best = v.x; bi = 2 * c; }
+                if (v.y > best) { best = v.y; bi = 2 * c + 1; }
+            }
         label[rowbase + x] = bi;
         if (prob) {
+            const float* s = sc + x * C;
             float sum = 0.f;
             for (int c = 0; c < C; c++) sum += expf(s[c] - best);
             float* pr = prob + (rowbase + x) * C;
@@ -243,15 +375,21 @@ extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const v
                                  const float* w_score, const float* w_vertex, int B, int h, int w, int Cs, int Cv, int C,
                                  float* out, void* stream)
 {
-    PCNN_REQUIRE(score4 && score5 && vert4 && vert5 && w_score && w_vertex && out, "lowres_heads: NULL tensor pointer");
+    PCNN_REQUIRE(score4 && score5 && vert4 && vert5 && w_score && out, "lowres_heads: NULL tensor pointer");
+    const bool folded = w_vertex == nullptr;
+    PCNN_REQUIRE(!folded || (3 * C <= Cv && Cv % 4 == 0), "lowres_heads: folded vertex head needs 3C <= Cv (got C = %d, Cv = %d)", C, Cv);
     PCNN_REQUIRE(h % 2 == 0 && w % 2 == 0, "lowres_heads: conv4 resolution must be even (got %d x %d)", h, w);
-    size_t smem = sizeof(float) * ((size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrWarps * 2 * (Cs + Cv));
+    PCNN_REQUIRE(Cs >= 4 && Cs % 4 == 0 && Cv % Cs == 0 && ((Cv / Cs) & (Cv / Cs - 1)) == 0,
+                 "lowres_heads: need Cs %% 4 == 0 and Cv = 2^k Cs (got %d, %d)", Cs, Cv);
+    PCNN_REQUIRE(C >= 1 && Cv / Cs <= 32, "lowres_heads: bad channel counts");
+    size_t smem = sizeof(float) * (folded ? (size_t)Cs * C + (size_t)kLrWarps * kLrPix * Cs
+                                          : (size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrWarps * kLrPix * (Cs + Cv));
     PCNN_REQUIRE(smem <= 200 * 1024, "lowres_heads: weights do not fit shared memory");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_lowres_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     PCNN_REQUIRE((long long)B * h * w < 0x7fffffffLL, "lowres_heads: too many pixels");
     size_t npix = (size_t)B * h * w;
-    int blocks = (int)std::min<size_t>((npix + 2 * kLrWarps - 1) / (2 * kLrWarps), (size_t)kNumSMs * 4);
+    int blocks = (int)std::min<size_t>((npix + kLrPix * kLrWarps - 1) / (kLrPix * kLrWarps), (size_t)kNumSMs * (folded ? 8 : 2));
     k_lowres_heads<<<blocks, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)score4, (const __nv_bfloat16*)score5,
                                                                (const __nv_bfloat16*)vert4, (const __nv_bfloat16*)vert5, w_score,
                                                                w_vertex, B, h, w, Cs, Cv, C, out);
@@ -268,11 +406,19 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
     int seg_cells = w <= 20 ? w : 20;  // 160 output pixels per CTA
     size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: segment does not fit shared memory (C = %d)", C);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_up8_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     dim3 grid(8 * h, B, (w + seg_cells - 1) / seg_cells);
-    k_up8_heads<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, seg_cells, label, vertex, prob,
-                                                           score);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_up8_heads<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_up8_heads<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    if (C == 22)   // the YCB / LOV class count (lov_color_2d.yml:14): compile-time strides
+        k_up8_heads<22><<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, seg_cells, label, vertex,
+                                                                   prob, score);
+    else
+        k_up8_heads<0><<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, seg_cells, label, vertex,
+                                                                  prob, score);
     return check_launch("up8_heads");
 }
 

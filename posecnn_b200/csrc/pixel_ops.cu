@@ -147,6 +147,69 @@ k_roi_pool_fwd_bf16(const __nv_bfloat16* __restrict__ bottom, const float* __res
     }
 }
 
+// Sliced variant (channels % 64 == 0): the cells of a bin are dealt round-robin to 4 lanes, which then merge their
+// (max, index) pairs by shuffle -- "larger value, on ties the smaller index" reproduces the reference's raster-order
+// scan with a strict '>' (.cu.cc:66-79).  Lane layout inside a warp: 8 consecutive channel groups (128 contiguous
+// bytes of one pixel) x 4 slices, so short bins and long bins both keep many loads in flight.
+__global__ void __launch_bounds__(256)
+k_roi_pool_fwd_bf16_s4(const __nv_bfloat16* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois,
+                       int batch, int height, int width, int channels, int ph_n, int pw_n, float scale,
+                       float* __restrict__ top, int* __restrict__ argmax)
+{
+    const int cg8 = channels / 64;                                  // blocks of 8 channel groups
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & 7, slice = lane >> 3;
+    const int nwork = num_rois * ph_n * pw_n * cg8;                // one warp-task = (roi, bin, block of 64 channels)
+    for (int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < nwork; task += (gridDim.x * blockDim.x) >> 5) {
+        const int gb = task % cg8;
+        int r1 = task / cg8;
+        const int pw = r1 % pw_n; r1 /= pw_n;
+        const int ph = r1 % ph_n;
+        const int n = r1 / ph_n;
+        const int ch0 = (gb * 8 + gl) * 8;
+        RoiBin rb = roi_bin(rois + (size_t)n * channel_rois, ph, pw, ph_n, pw_n, scale, height, width);
+        const bool empty = (rb.he <= rb.hs) || (rb.we <= rb.ws) || rb.b < 0 || rb.b >= batch;
+        float mv[8];
+        int mi[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { mv[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
+        if (!empty) {
+            const __nv_bfloat16* img = bottom + (size_t)rb.b * height * width * channels;
+            const int bw = rb.we - rb.ws, cells = bw * (rb.he - rb.hs);
+#pragma unroll 2
+            for (int i = slice; i < cells; i += 4) {
+                const int hh = i / bw, ww = i - hh * bw;
+                const int bi = ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0;
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + bi));
+                const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 f = __bfloat1622float2(q2[k]);
+                    if (f.x > mv[2 * k]) { mv[2 * k] = f.x; mi[2 * k] = bi + 2 * k; }
+                    if (f.y > mv[2 * k + 1]) { mv[2 * k + 1] = f.y; mi[2 * k + 1] = bi + 2 * k + 1; }
+                }
+            }
+#pragma unroll
+            for (int d = 8; d <= 16; d <<= 1) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, mv[k], d);
+                    const int oi = __shfl_xor_sync(0xffffffffu, mi[k], d);
+                    // a slice that saw no cell still holds (-FLT_MAX, -1): never wins against a real cell
+                    if (oi >= 0 && (ov > mv[k] || (ov == mv[k] && (mi[k] < 0 || oi < mi[k])))) { mv[k] = ov; mi[k] = oi; }
+                }
+            }
+        }
+        if (slice == 0) {
+            const size_t o = ((size_t)(n * ph_n + ph) * pw_n + pw) * channels + ch0;
+            *reinterpret_cast<float4*>(top + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+            *reinterpret_cast<float4*>(top + o + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+            *reinterpret_cast<int4*>(argmax + o) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+            *reinterpret_cast<int4*>(argmax + o + 4) = make_int4(mi[4], mi[5], mi[6], mi[7]);
+        }
+    }
+}
+
 // pool_channel mode: one output channel = channel roi_cls of the input (.cu.cc:84-87)
 __global__ void __launch_bounds__(256)
 k_roi_pool_fwd_cls(const float* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois,
@@ -694,6 +757,13 @@ extern "C" int pcnn_roi_pool_fwd_bf16(const void* bottom_bf16, const float* rois
     PCNN_REQUIRE(channel_rois >= 6 && channels % 8 == 0, "roi_pool_bf16: needs >= 6 roi columns and channels %% 8 == 0");
     if (num_rois == 0 || pooled_height == 0 || pooled_width == 0) return PCNN_OK;
     size_t total = (size_t)num_rois * pooled_height * pooled_width * (channels / 8);
+    if (channels % 64 == 0 && (long long)num_rois * pooled_height * pooled_width * (channels / 64) * 32 < 0x7fffffffLL) {
+        size_t threads = (size_t)num_rois * pooled_height * pooled_width * (channels / 64) * 32;
+        k_roi_pool_fwd_bf16_s4<<<grid_for(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)bottom_bf16, rois, num_rois, channel_rois, batch, height, width, channels, pooled_height,
+            pooled_width, spatial_scale, top, argmax);
+        return check_launch("roi_pool_fwd_bf16_s4");
+    }
     k_roi_pool_fwd_bf16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)bottom_bf16, rois, num_rois, channel_rois, batch, height, width, channels, pooled_height,
         pooled_width, spatial_scale, top, argmax);

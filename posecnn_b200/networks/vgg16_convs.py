@@ -35,8 +35,12 @@ VGG_CFG = [("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool1", ("conv2_1", 64, 128
 class vgg16_convs:
     def __init__(self, input_format="COLOR", num_classes=22, num_units=64, scales=(1.0,), threshold_label=1.0,
                  vote_threshold=-1.0, vertex_reg_2d=True, vertex_reg_3d=False, pose_reg=True, adaptation=False,
-                 trainable=True, is_train=False, device="cuda"):
+                 trainable=True, is_train=False, device="cuda", fold_vertex_head=True):
         self.input_format = input_format
+        # fold_vertex_head: multiply the vertex_pred matrix (128 -> 3C) into score_conv4_vertex / score_conv5_vertex
+        # (512 -> 128) once at prepare() time; exact algebra (no non-linearity between them, vgg16_convs.py:151-163),
+        # removes 86 % of the 1/8-resolution matrix work.  False keeps the reference's intermediate layers.
+        self.fold_vertex_head = bool(fold_vertex_head) and 3 * num_classes <= 128
         self.num_classes = num_classes
         self.num_units = num_units
         self.threshold_label = threshold_label
@@ -147,8 +151,19 @@ class vgg16_convs:
                 T[name] = conv.hwio_to_tc(w)
         for name in ("fc6", "fc7", "fc8"):
             T[f"{name}/weights"] = P[f"{name}/weights"].t().contiguous().to(torch.bfloat16)  # [out, in] for F.linear
+            T[f"{name}/biases"] = P[f"{name}/biases"].to(torch.bfloat16)
         T["score/w"] = P["score/weights"].reshape(self.num_units, self.num_classes).contiguous()
         T["vertex_pred/w"] = P["vertex_pred/weights"].reshape(128, 3 * self.num_classes).contiguous()
+        if self.fold_vertex_head:
+            Wp = T["vertex_pred/w"].double()
+            for name in ("score_conv4_vertex", "score_conv5_vertex"):
+                w = P[f"{name}/weights"].reshape(-1, 128).double() @ Wp              # [512, 3C]
+                b = P[f"{name}/biases"].double() @ Wp                                # [3C]
+                wpad = torch.zeros((1, 1, w.shape[0], 128), dtype=torch.float32, device=w.device)
+                wpad[0, 0, :, :w.shape[1]] = w.float()
+                bpad = torch.zeros((128,), dtype=torch.float32, device=w.device)
+                bpad[:b.shape[0]] = b.float()
+                T[f"{name}/folded_weights"], T[f"{name}/folded_biases"] = conv.hwio_to_tc(wpad), bpad
 
     # ------------------------------------------------------------------ graph pieces
     def _trunk(self, data, sfx=""):
@@ -197,12 +212,19 @@ class vgg16_convs:
         # 1x1 convolutions on the tensor cores (score_conv4/5 have a ReLU, the vertex ones do not)
         s5 = conv.conv_bf16(h5, T["score_conv5/weights"], P["score_conv5/biases"], 1, True)
         s4 = conv.conv_bf16(h4, T["score_conv4/weights"], P["score_conv4/biases"], 1, True)
-        v5 = conv.conv_bf16(c5, T["score_conv5_vertex/weights"], P["score_conv5_vertex/biases"], 1, False)
-        v4 = conv.conv_bf16(c4, T["score_conv4_vertex/weights"], P["score_conv4_vertex/biases"], 1, False)
-        L["score_conv4"], L["score_conv5"], L["score_conv4_vertex"], L["score_conv5_vertex"] = s4, s5, v4, v5
+        L["score_conv4"], L["score_conv5"] = s4, s5
+        if self.fold_vertex_head:
+            v5 = conv.conv_bf16(c5, T["score_conv5_vertex/folded_weights"], T["score_conv5_vertex/folded_biases"], 1, False)
+            v4 = conv.conv_bf16(c4, T["score_conv4_vertex/folded_weights"], T["score_conv4_vertex/folded_biases"], 1, False)
+            w_vertex = None
+        else:
+            v5 = conv.conv_bf16(c5, T["score_conv5_vertex/weights"], P["score_conv5_vertex/biases"], 1, False)
+            v4 = conv.conv_bf16(c4, T["score_conv4_vertex/weights"], P["score_conv4_vertex/biases"], 1, False)
+            L["score_conv4_vertex"], L["score_conv5_vertex"] = v4, v5
+            w_vertex = T["vertex_pred/w"]
         h, w = H // 8, W // 8
         lowres = torch.empty((B, h, w, 4 * C), dtype=torch.float32, device=data.device)
-        check(lib().pcnn_lowres_heads(ptr(s4), ptr(s5), ptr(v4), ptr(v5), ptr(T["score/w"]), ptr(T["vertex_pred/w"]), B, h, w,
+        check(lib().pcnn_lowres_heads(ptr(s4), ptr(s5), ptr(v4), ptr(v5), ptr(T["score/w"]), ptr(w_vertex), B, h, w,
                                       self.num_units, 128, C, ptr(lowres), stream()))
         self._last_lowres = lowres
         label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
@@ -226,9 +248,9 @@ class vgg16_convs:
             p5, _ = roi_pooling_op.roi_pool(c5, rois, 7, 7, 1.0 / 16.0, 0)
             p4, _ = roi_pooling_op.roi_pool(c4, rois, 7, 7, 1.0 / 8.0, 0)
             x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                     # pool_score, flatten (h, w, c)
-            x = torch.relu(torch.nn.functional.linear(x, T["fc6/weights"], P["fc6/biases"].to(torch.bfloat16)))
-            x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], P["fc7/biases"].to(torch.bfloat16)))
-            x = torch.nn.functional.linear(x, T["fc8/weights"], P["fc8/biases"].to(torch.bfloat16)).float()
+            x = torch.relu(torch.nn.functional.linear(x, T["fc6/weights"], T["fc6/biases"]))
+            x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], T["fc7/biases"]))
+            x = torch.nn.functional.linear(x, T["fc8/weights"], T["fc8/biases"]).float()
             L["poses_tanh"] = torch.tanh(x)
         if sync_rois:
             n = max(1, int(num_rois.item()))  # the one host read the op's data-dependent shape requires

@@ -20,7 +20,8 @@ def rel_l2(a, b):
 @pytest.fixture(scope="module")
 def net_and_out(cuda):
     from posecnn_b200.networks.vgg16_convs import vgg16_convs
-    net = vgg16_convs(num_classes=6, device=cuda).init_random(seed=0, bias_std=0.05)
+    # fold_vertex_head=False keeps the reference's intermediate layers (score_conv*_vertex) for the staged checks
+    net = vgg16_convs(num_classes=6, device=cuda, fold_vertex_head=False).init_random(seed=0, bias_std=0.05)
     rgb, _ = synth.make_images(2, 64, 96, seed=3)
     data = torch.from_numpy(rgb).to(cuda)
     meta = torch.from_numpy(np.stack([synth.make_meta(synth.intrinsics(64, 96))] * 2)).to(cuda)
@@ -120,3 +121,77 @@ def test_rgbd_two_trunk_network(cuda):
     assert rel_l2(out["vertex_pred"].permute(0, 3, 1, 2), vertex) < 2e-2
     got_s4 = out["score_conv4"].float().permute(0, 3, 1, 2)
     assert rel_l2(got_s4, s4) < 2e-2
+
+
+@pytest.mark.parametrize("C", [2, 6, 22, 30])
+def test_lowres_heads_kernel(cuda, C):
+    """pcnn_lowres_heads alone (register-tiled column map: full vertex passes, then score columns next to split
+    left-over vertex columns) against torch fp32: add = conv4 branch + up2(conv5 branch), then the two 1x1 matrices."""
+    from posecnn_b200._lib import lib, check, ptr, stream
+    g = torch.Generator(device="cpu").manual_seed(C)
+    B, h, w, Cs, Cv = 2, 6, 10, 64, 128      # 120 pixels: 15 groups of 8; also run a ragged count below
+    for (hh, ww) in ((h, w), (2, 6)):         # 24 px = 3 groups; B*hh*ww not a multiple of 8 when B = 1
+        for Bn in (B, 1):
+            mk = lambda *s: torch.randn(*s, generator=g).to(cuda)
+            s4, s5 = mk(Bn, hh, ww, Cs).bfloat16(), mk(Bn, hh // 2, ww // 2, Cs).bfloat16()
+            v4, v5 = mk(Bn, hh, ww, Cv).bfloat16(), mk(Bn, hh // 2, ww // 2, Cv).bfloat16()
+            Ws, Wv = mk(Cs, C) * 0.1, mk(Cv, 3 * C) * 0.1
+            out = torch.empty((Bn, hh, ww, 4 * C), dtype=torch.float32, device=cuda)
+            check(lib().pcnn_lowres_heads(ptr(s4), ptr(s5), ptr(v4), ptr(v5), ptr(Ws), ptr(Wv), Bn, hh, ww, Cs, Cv, C, ptr(out), stream()))
+            nchw = lambda t: t.float().permute(0, 3, 1, 2)
+            add_s = nchw(s4) + R.deconv(nchw(s5), 4, 2)
+            add_v = nchw(v4) + R.deconv(nchw(v5), 4, 2)
+            want = torch.cat([torch.einsum("nkhw,kc->nhwc", add_s, Ws), torch.einsum("nkhw,kc->nhwc", add_v, Wv)], 3)
+            assert torch.allclose(out, want, rtol=1e-4, atol=1e-4), (C, Bn, hh, ww, (out - want).abs().max().item())
+
+
+@pytest.mark.parametrize("C", [6, 22])
+def test_folded_vertex_head(cuda, C):
+    """Default network: vertex_pred (128 -> 3C) multiplied into the two vertex 1x1 convolutions at prepare() time.
+    Same parameters as the un-folded network -> identical labels (score branch untouched), vertex_pred equal up to the
+    bf16 rounding point moving from the 128-channel intermediates to the 3C outputs, and within the stated 2e-2 of the
+    fp32 reference graph."""
+    from posecnn_b200.networks.vgg16_convs import vgg16_convs
+    rgb, _ = synth.make_images(2, 64, 96, seed=3)
+    data = torch.from_numpy(rgb).to(cuda)
+    meta = torch.from_numpy(np.stack([synth.make_meta(synth.intrinsics(64, 96))] * 2)).to(cuda)
+    ext = torch.from_numpy(synth.extents_for(C)).to(cuda)
+    outs = []
+    for fold in (False, True):
+        net = vgg16_convs(num_classes=C, device=cuda, fold_vertex_head=fold).init_random(seed=0, bias_std=0.05)
+        assert net.fold_vertex_head == fold
+        outs.append(dict(net.forward(data, meta, ext)))
+    a, b = outs
+    assert "score_conv4_vertex" in a and "score_conv4_vertex" not in b
+    assert torch.equal(a["label_2d"], b["label_2d"])
+    assert rel_l2(b["vertex_pred"], a["vertex_pred"]) < 1e-2
+    x = (data.float() - torch.tensor([102.9801, 115.9465, 122.7717], device=data.device)).permute(0, 3, 1, 2)
+    feats = R.trunk(net.params, x)
+    _, _, _, vertex = R.heads(net.params, feats["conv4_3"], feats["conv5_3"], C)
+    assert rel_l2(b["vertex_pred"].permute(0, 3, 1, 2), vertex) < 2e-2
+
+
+@pytest.mark.parametrize("C", [22, 6])
+def test_up8_heads_kernel(cuda, C):
+    """pcnn_up8_heads alone (C = 22 is the compile-time-stride specialisation) against the dense transposed
+    convolution of the reference graph: bilinear x8 of the low-resolution maps, + bias, ReLU / arg-max / softmax."""
+    from posecnn_b200._lib import lib, check, ptr, stream
+    g = torch.Generator(device="cpu").manual_seed(100 + C)
+    B, h, w = 2, 5, 23                           # 23 cells: one full 20-cell segment + a ragged one
+    lowres = torch.randn(B, h, w, 4 * C, generator=g).to(cuda)
+    bs, bv = torch.randn(C, generator=g).to(cuda), torch.randn(3 * C, generator=g).to(cuda)
+    H, W = 8 * h, 8 * w
+    label = torch.empty((B, H, W), dtype=torch.int32, device=cuda)
+    vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=cuda)
+    prob = torch.empty((B, H, W, C), dtype=torch.float32, device=cuda)
+    score = torch.empty((B, H, W, C), dtype=torch.float32, device=cuda)
+    check(lib().pcnn_up8_heads(ptr(lowres), ptr(bs), ptr(bv), B, h, w, C, ptr(label), ptr(vertex), ptr(prob), ptr(score), stream()))
+    up = R.deconv(lowres.permute(0, 3, 1, 2), 16, 8).permute(0, 2, 3, 1)
+    want_s = torch.relu(up[..., :C] + bs)
+    want_v = up[..., C:] + bv
+    assert torch.allclose(vertex, want_v, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(score, want_s, rtol=1e-5, atol=1e-5)
+    assert torch.equal(label, torch.argmax(score, dim=3).to(torch.int32))          # arg-max of the kernel's own scores: exact
+    first = (score == score.max(dim=3, keepdim=True).values).float().argmax(dim=3)  # lowest index on ties
+    assert torch.equal(label.long(), first)
+    assert torch.allclose(prob, torch.softmax(score, dim=3), atol=1e-6)

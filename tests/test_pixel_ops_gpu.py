@@ -113,3 +113,21 @@ def test_average_distance(cuda, P, N):
     l, _ = opg.average_distance_loss(pr, *a[1:], 0.01)
     (3.0 * l).sum().backward()
     np.testing.assert_allclose(to_np(pr.grad), 3.0 * to_np(diff), rtol=1e-6)         # AveragedistanceGrad = upstream * diff
+
+
+@pytest.mark.parametrize("channels", [512, 128, 72])
+def test_roi_pool_bf16_features_with_ties(cuda, channels):
+    """bf16 feature maps (what the tensor-core trunk hands over): channels % 64 == 0 takes the sliced kernel whose
+    shuffle merge must reproduce the raster-order first-maximum rule.  Small-integer features force many ties."""
+    from posecnn_b200.roi_pooling_layer import roi_pooling_op as op
+    rng = np.random.default_rng(7)
+    B, h, w = 2, 60, 80
+    data = rng.integers(-2, 3, size=(B, h, w, channels)).astype(np.float32)      # exactly representable in bf16
+    rois = synth.make_rois(23, B, num_classes=22, seed=9)
+    rois[0, 2:6] = [0, 0, 639, 479]              # whole image: large bins
+    rois[1, 2:6] = [16, 16, 23, 23]              # one feature cell
+    rois[2, 2:6] = [900, 900, 910, 910]          # outside
+    top_w, arg_w = oracle.roi_pool(data, rois, 7, 7, 1.0 / 8.0, 0)
+    top, arg = op.roi_pool(T(data, cuda).to(torch.bfloat16), T(rois, cuda), 7, 7, 1.0 / 8.0, 0)
+    np.testing.assert_array_equal(to_np(arg), arg_w)
+    np.testing.assert_array_equal(to_np(top), top_w)
