@@ -176,6 +176,7 @@ struct ConvParams {
     int B, H, W, Cin, Cout;
     int taps, ksize;          // 9 / 3 or 1 / 1
     int tiles_h, tiles_w, n_tiles_n, total_tiles;
+    int tile_h, tile_w;       // k_conv_tc: pixel tile (tile_h * tile_w = 128; 8 x 16, or 16 x 8 when that wastes fewer pixels)
     int relu;
     int pool;                 // 1: the epilogue applies the 2x2 / stride-2 max pool and stores ONLY the pooled tensor
     const float* bias;
@@ -238,7 +239,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
                 const int tw = rest % p.tiles_w; rest /= p.tiles_w;
                 const int th = rest % p.tiles_h;
                 const int img = rest / p.tiles_h;
-                const int h0 = th * kTileH, w0 = tw * kTileW, n0 = nt * BN;
+                const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = nt * BN;
                 const int pad = p.ksize / 2;
                 for (int ks = 0; ks < ksteps; ks++) {
                     const int tap = ks / kchunks, c0 = (ks % kchunks) * kKC;
@@ -290,7 +291,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
             const int tw = rest % p.tiles_w; rest /= p.tiles_w;
             const int th = rest % p.tiles_h;
             const int img = rest / p.tiles_h;
-            const int h0 = th * kTileH, w0 = tw * kTileW, n0 = nt * BN;
+            const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = nt * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull[acc], acc_phase);
@@ -627,14 +628,19 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
 
 // ---------------------------------------------------------------------------------------------
 // First layer (conv1_1, Cin = 3, K = 27 -> 32) on the tensor cores with the im2col done in shared memory:
-// warps 4-11 (two groups, alternating tiles) build the A tile of an 8x16 pixel tile straight from the uint8 / f32 image (pre-processing
-// `BGR - PIXEL_MEANS` fused, zero outside the image = SAME padding) in the swizzled K-major layout, warp 12
-// issues two K = 16 UMMAs per tile against the resident 64 x 64 weight tile, warps 0-3 run the usual
-// epilogue.  No im2col tensor ever exists in HBM.
+// warps 8-23 (four groups, round-robin over tiles) build the A tile of an 8x16 pixel tile straight from the uint8 / f32
+// image (pre-processing `BGR - PIXEL_MEANS` fused, zero outside the image = SAME padding) in the swizzled K-major
+// layout, warp 24 issues two K = 16 UMMAs per tile against the resident 64 x 64 weight tile, warps 0-7 are two
+// epilogue groups, one per TMEM accumulator.  No im2col tensor ever exists in HBM.
+// The layer is a 1.26 GB write with almost no math: per tile the builder (27 dependent-free byte loads, ~1 us) and
+// the epilogue (TMEM load -> pack -> TMA store) are latency chains, so the kernel keeps four builds and two
+// epilogues in flight per SM (ncu on the 2-builder / 1-epilogue version: issue slots 44 % busy, 0.9 us per tile).
 // ---------------------------------------------------------------------------------------------
 constexpr int kC1Stages = 6;
-constexpr int kC1Threads = 416;  // 4 epilogue warps, 2 x 4 A-builder warps (alternating tiles), 1 MMA warp
-constexpr int kC1BarOff = kC1Stages * kABytes + 64 * 128 + 2 * kStageBytes;
+constexpr int kC1EpiGroups = 2, kC1BuildGroups = 4;
+constexpr int kC1Threads = 128 * (kC1EpiGroups + kC1BuildGroups) + 32;  // 8 epilogue warps, 16 A-builder warps, 1 MMA warp
+constexpr int kC1MmaWarp = 4 * (kC1EpiGroups + kC1BuildGroups);
+constexpr int kC1BarOff = kC1Stages * kABytes + 64 * 128 + kC1EpiGroups * 2 * kStageBytes;
 constexpr int kC1Smem = kC1BarOff + 256 + 1024;
 
 template <typename TIn>
@@ -656,7 +662,7 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
 
-    if (warp == 12 && lane == 0) {
+    if (warp == kC1MmaWarp && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         for (int s = 0; s < kC1Stages; s++) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
@@ -664,20 +670,20 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(tmem_holder, kTmemCols);
+    if (warp == kC1MmaWarp) tmem_alloc(tmem_holder, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    if (warp >= 4 && warp < 12) {
-        // ===================== A builders: one tile row (pixel) per thread; two groups take alternating tiles =====================
-        const int group = (threadIdx.x - 128) >> 7;
-        const int r = (threadIdx.x - 128) & 127;
+    if (warp >= 4 * kC1EpiGroups && warp < kC1MmaWarp) {
+        // ===================== A builders: one tile row (pixel) per thread; the groups take tiles round-robin =====================
+        const int group = (threadIdx.x - 128 * kC1EpiGroups) >> 7;
+        const int r = (threadIdx.x - 128 * kC1EpiGroups) & 127;
         const int hl = r >> 4, wl = r & 15;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-            if ((it & 1) != group) continue;
+            if (it % kC1BuildGroups != group) continue;
             const int stage = it % kC1Stages;
             const uint32_t phase = (it / kC1Stages) & 1;
             const int tw = tile % p.tiles_w;
@@ -686,8 +692,11 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             const int y = th * kTileH + hl, x = tw * kTileW + wl;
             const TIn* base = in + (size_t)img * p.H * p.W * 3;
             float v[32];
+            // K = 27, 28 carry 1.0: the matching weight rows hold the bias (bf16 hi + lo parts, patched into the
+            // resident weight tile by the MMA warp), so the bias add happens inside the MMA
+            v[27] = 1.f; v[28] = 1.f;
 #pragma unroll
-            for (int k = 27; k < 32; k++) v[k] = 0.f;
+            for (int k = 29; k < 32; k++) v[k] = 0.f;
 #pragma unroll
             for (int dy = 0; dy < 3; dy++) {
                 const int yy = y + dy - 1;
@@ -718,12 +727,28 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
         }
-    } else if (warp == 12) {
+    } else if (warp == kC1MmaWarp) {
         // ===================== MMA issuer (+ one-time weight load) =====================
         if (elect_one()) {
             mbar_arrive_expect_tx(wbar, 64 * 128);
             tma_load_2d(sb, &map_w, wbar, 0, 0);
-            mbar_wait(wbar, 0);
+        }
+        __syncwarp();
+        mbar_wait(wbar, 0);   // every lane observes the completed TMA before it patches the tile
+        // bias -> weight rows K = 27 (bf16 of the bias) and K = 28 (bf16 of the remainder), swizzled K-major layout:
+        // element k of output channel n sits at n * 128 + ((k / 8) ^ (n & 7)) * 16 + (k % 8) * 2
+        __syncwarp();
+        for (int n = lane; n < BN; n += 32) {
+            const float bv = p.bias[n];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+            uint8_t* rowp = sb + n * 128 + ((3 ^ (n & 7)) << 4);
+            *reinterpret_cast<__nv_bfloat16*>(rowp + 6) = hi;    // k = 27
+            *reinterpret_cast<__nv_bfloat16*>(rowp + 8) = lo;    // k = 28
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(BN);
             const uint64_t db = make_desc(smem_u32(sb));
             int stage = 0;
@@ -744,36 +769,40 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             }
         }
     } else {
-        // ===================== epilogue warps 0..3 (same as k_conv_tc, BN = 64) =====================
+        // ===================== epilogue: group g = warps 4g..4g+3 owns TMEM accumulator g (tiles with it & 1 == g) =====================
         int it = 0, obuf = 0;
-        const int row = warp * 32 + lane;
+        const int eg = warp >> 2, wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const bool issuer = (threadIdx.x & 127) == 0;
+        uint8_t* my_stage = out_stage + eg * 2 * kStageBytes;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            if ((it & 1) != eg) continue;
             const int tw = tile % p.tiles_w;
             const int rest = tile / p.tiles_w;
             const int th = rest % p.tiles_h, img = rest / p.tiles_h;
-            const int acc = it & 1;
+            const int acc = eg;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
-            if (threadIdx.x == 0) tma_store_wait_read<1>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            uint8_t* ob = out_stage + obuf * kStageBytes;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
+            if (issuer) tma_store_wait_read<1>();
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            uint8_t* ob = my_stage + obuf * kStageBytes;
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 uint32_t rr[32];
                 tmem_ld_32x32(t_addr + half * 32, rr);
                 tmem_ld_wait();
-                const float* bias = p.bias + half * 32;
+                const __nv_bfloat162 floor2 = __floats2bfloat162_rn(p.relu ? 0.f : -INFINITY, p.relu ? 0.f : -INFINITY);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     uint32_t packed[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        float v0 = __uint_as_float(rr[j * 8 + q * 2]) + __ldg(bias + j * 8 + q * 2);
-                        float v1 = __uint_as_float(rr[j * 8 + q * 2 + 1]) + __ldg(bias + j * 8 + q * 2 + 1);
-                        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                        // bias already inside the accumulator; ReLU on the packed pair (rounding is monotone, 0 is exact)
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(rr[j * 8 + q * 2]), __uint_as_float(rr[j * 8 + q * 2 + 1]));
+                        b2 = __hmax2(b2, floor2);
                         packed[q] = *reinterpret_cast<uint32_t*>(&b2);
                     }
                     const int piece = half * 4 + j;
@@ -784,18 +813,19 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 0) {
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (issuer) {
                 tma_store_4d(&map_out, ob, 0, tw * kTileW, th * kTileH, img);
                 tma_store_commit();
             }
             obuf ^= 1;
         }
-        if (threadIdx.x == 0) tma_store_wait_all();
+        if (issuer) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kC1MmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1056,6 +1086,7 @@ static int conv_bf16_tc_impl(const void* in, const void* weights, const float* b
         if (rc) return rc;
         ConvParams p;
         p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ksize = 3; p.taps = 9;
+        p.tile_h = 2; p.tile_w = kRowPx;
         p.tiles_h = H / 2;
         p.tiles_w = (W + kRowPx - 1) / kRowPx;
         p.n_tiles_n = Cout / bn;
@@ -1064,17 +1095,24 @@ static int conv_bf16_tc_impl(const void* in, const void* weights, const float* b
         if (resb && p.total_tiles >= p.n_tiles_n) return launch_conv_row2<64, true>(mi, mw, mo, p, sms, st);
         return bn == 128 ? launch_conv_row2<128, false>(mi, mw, mo, p, sms, st) : launch_conv_row2<64, false>(mi, mw, mo, p, sms, st);
     }
-    rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC);
+    // pixel tile: 8 x 16, or 16 x 8 when that covers the map with fewer tiles (conv5: 30 x 40 -> 10 tiles instead of 12).
+    // The tile's pixel order is whatever the TMA box says (row = h * tile_w + w for load and store alike), so only
+    // the box shape and the tile origin change; the fused pool epilogue is written for 8 x 16.
+    int tile_h = kTileH, tile_w = kTileW;
+    if (!pool && ((H + 15) / 16) * ((W + 7) / 8) < ((H + 7) / 8) * ((W + 15) / 16)) { tile_h = 16; tile_w = 8; }
+    rc = make_map_nhwc(&mi, in, B, H, W, Cin, kKC, tile_w, tile_h);
     if (rc) return rc;
     rc = make_map_weights(&mw, weights, ksize * ksize * Cin, Cout, bn);
     if (rc) return rc;
-    rc = pool ? make_map_nhwc(&mo, out, B, H / 2, W / 2, Cout, 64, kTileW / 2, kTileH / 2) : make_map_nhwc(&mo, out, B, H, W, Cout, 64);
+    rc = pool ? make_map_nhwc(&mo, out, B, H / 2, W / 2, Cout, 64, kTileW / 2, kTileH / 2)
+              : make_map_nhwc(&mo, out, B, H, W, Cout, 64, tile_w, tile_h);
     if (rc) return rc;
     ConvParams p;
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
     p.ksize = ksize; p.taps = ksize * ksize;
-    p.tiles_h = (H + kTileH - 1) / kTileH;
-    p.tiles_w = (W + kTileW - 1) / kTileW;
+    p.tile_h = tile_h; p.tile_w = tile_w;
+    p.tiles_h = (H + tile_h - 1) / tile_h;
+    p.tiles_w = (W + tile_w - 1) / tile_w;
     p.n_tiles_n = Cout / bn;
     p.total_tiles = B * p.tiles_h * p.tiles_w * p.n_tiles_n;
     p.relu = relu;
@@ -1142,6 +1180,7 @@ extern "C" int pcnn_conv1_fused_tc(const void* in, int in_is_u8, const float* me
     if (rc) return rc;
     ConvParams p;
     p.B = B; p.H = H; p.W = W; p.Cin = 3; p.Cout = 64; p.ksize = 3; p.taps = 9;
+    p.tile_h = kTileH; p.tile_w = kTileW;
     p.tiles_h = (H + kTileH - 1) / kTileH;
     p.tiles_w = (W + kTileW - 1) / kTileW;
     p.n_tiles_n = 1;

@@ -147,26 +147,28 @@ k_roi_pool_fwd_bf16(const __nv_bfloat16* __restrict__ bottom, const float* __res
     }
 }
 
-// Sliced variant (channels % 64 == 0): the cells of a bin are dealt round-robin to 4 lanes, which then merge their
-// (max, index) pairs by shuffle -- "larger value, on ties the smaller index" reproduces the reference's raster-order
-// scan with a strict '>' (.cu.cc:66-79).  Lane layout inside a warp: 8 consecutive channel groups (128 contiguous
-// bytes of one pixel) x 4 slices, so short bins and long bins both keep many loads in flight.
+// Sliced variant (channels % 32 == 0): the cells of a bin are dealt round-robin to 8 slices of 4 lanes (4 x 8 channels
+// = 64 contiguous bytes of one pixel), four loads in flight per lane, and the (max, index) pairs are merged by
+// shuffle -- "larger value, on ties the smaller index" reproduces the reference's raster-order scan with a strict '>'
+// (.cu.cc:66-79).  A whole-image ROI has ~100 cells per bin at 1/8 resolution: the serial chain per lane is what
+// bounded the one-thread-per-bin kernel (ncu: long-scoreboard 8.7 warps per issue).
+constexpr int kRoiSlices = 8;
 __global__ void __launch_bounds__(256)
 k_roi_pool_fwd_bf16_s4(const __nv_bfloat16* __restrict__ bottom, const float* __restrict__ rois, int num_rois, int channel_rois,
                        int batch, int height, int width, int channels, int ph_n, int pw_n, float scale,
                        float* __restrict__ top, int* __restrict__ argmax)
 {
-    const int cg8 = channels / 64;                                  // blocks of 8 channel groups
+    const int cgb = channels / 32;                                  // blocks of 4 channel groups (32 channels)
     const int lane = threadIdx.x & 31;
-    const int gl = lane & 7, slice = lane >> 3;
-    const int nwork = num_rois * ph_n * pw_n * cg8;                // one warp-task = (roi, bin, block of 64 channels)
+    const int gl = lane & 3, slice = lane >> 2;
+    const int nwork = num_rois * ph_n * pw_n * cgb;                // one warp-task = (roi, bin, block of 32 channels)
     for (int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < nwork; task += (gridDim.x * blockDim.x) >> 5) {
-        const int gb = task % cg8;
-        int r1 = task / cg8;
+        const int gb = task % cgb;
+        int r1 = task / cgb;
         const int pw = r1 % pw_n; r1 /= pw_n;
         const int ph = r1 % ph_n;
         const int n = r1 / ph_n;
-        const int ch0 = (gb * 8 + gl) * 8;
+        const int ch0 = (gb * 4 + gl) * 8;
         RoiBin rb = roi_bin(rois + (size_t)n * channel_rois, ph, pw, ph_n, pw_n, scale, height, width);
         const bool empty = (rb.he <= rb.hs) || (rb.we <= rb.ws) || rb.b < 0 || rb.b >= batch;
         float mv[8];
@@ -176,21 +178,31 @@ k_roi_pool_fwd_bf16_s4(const __nv_bfloat16* __restrict__ bottom, const float* __
         if (!empty) {
             const __nv_bfloat16* img = bottom + (size_t)rb.b * height * width * channels;
             const int bw = rb.we - rb.ws, cells = bw * (rb.he - rb.hs);
-#pragma unroll 2
-            for (int i = slice; i < cells; i += 4) {
-                const int hh = i / bw, ww = i - hh * bw;
-                const int bi = ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0;
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + bi));
-                const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+            for (int i0 = slice; i0 < cells; i0 += 4 * kRoiSlices) {
+                uint4 q[4];
+                int bi[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float2 f = __bfloat1622float2(q2[k]);
-                    if (f.x > mv[2 * k]) { mv[2 * k] = f.x; mi[2 * k] = bi + 2 * k; }
-                    if (f.y > mv[2 * k + 1]) { mv[2 * k + 1] = f.y; mi[2 * k + 1] = bi + 2 * k + 1; }
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * kRoiSlices;
+                    const int ic = min(i, cells - 1);
+                    const int hh = ic / bw, ww = ic - hh * bw;
+                    bi[u] = i < cells ? ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0 : -1;
+                    q[u] = __ldg(reinterpret_cast<const uint4*>(img + ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (bi[u] < 0) continue;
+                    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 f = __bfloat1622float2(q2[k]);
+                        if (f.x > mv[2 * k]) { mv[2 * k] = f.x; mi[2 * k] = bi[u] + 2 * k; }
+                        if (f.y > mv[2 * k + 1]) { mv[2 * k + 1] = f.y; mi[2 * k + 1] = bi[u] + 2 * k + 1; }
+                    }
                 }
             }
 #pragma unroll
-            for (int d = 8; d <= 16; d <<= 1) {
+            for (int d = 4; d <= 16; d <<= 1) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const float ov = __shfl_xor_sync(0xffffffffu, mv[k], d);
@@ -757,8 +769,8 @@ extern "C" int pcnn_roi_pool_fwd_bf16(const void* bottom_bf16, const float* rois
     PCNN_REQUIRE(channel_rois >= 6 && channels % 8 == 0, "roi_pool_bf16: needs >= 6 roi columns and channels %% 8 == 0");
     if (num_rois == 0 || pooled_height == 0 || pooled_width == 0) return PCNN_OK;
     size_t total = (size_t)num_rois * pooled_height * pooled_width * (channels / 8);
-    if (channels % 64 == 0 && (long long)num_rois * pooled_height * pooled_width * (channels / 64) * 32 < 0x7fffffffLL) {
-        size_t threads = (size_t)num_rois * pooled_height * pooled_width * (channels / 64) * 32;
+    if (channels % 32 == 0 && (long long)num_rois * pooled_height * pooled_width * (channels / 32) * 32 < 0x7fffffffLL) {
+        size_t threads = (size_t)num_rois * pooled_height * pooled_width * (channels / 32) * 32;
         k_roi_pool_fwd_bf16_s4<<<grid_for(threads, 256), 256, 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)bottom_bf16, rois, num_rois, channel_rois, batch, height, width, channels, pooled_height,
             pooled_width, spatial_scale, top, argmax);

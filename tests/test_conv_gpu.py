@@ -80,7 +80,10 @@ def test_conv_pool_fused(cuda, B, H, W, Cin, Cout, bn):
 
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
 def test_conv1_fused_matches_im2col_path(cuda, dtype):
-    """conv1_1 with the im2col built in shared memory == im2col kernel + 1x1 tensor-core conv (bit exact) == fp32 reference."""
+    """conv1_1 with the im2col built in shared memory vs the im2col kernel + 1x1 tensor-core conv, and vs the fp32 reference.
+    The fused kernel adds the bias inside the MMA (two spare K columns of ones x bias split into bf16 hi + lo, ~2^-17
+    relative), the un-fused path adds the fp32 bias in the epilogue: the bf16 outputs agree except for rare 1-ulp
+    rounding flips."""
     from posecnn_b200 import conv
     g = torch.Generator(device="cpu").manual_seed(5)
     B, H, W = 2, 37, 53
@@ -93,7 +96,8 @@ def test_conv1_fused_matches_im2col_path(cuda, dtype):
     got = conv.conv1_fused(x, wt, b, mean, True)
     want = conv.conv_bf16(conv.im2col_c3(x, mean), wt, b, 1, True)
     torch.cuda.synchronize()
-    assert torch.equal(got, want)
+    assert (got == want).float().mean().item() > 0.995
+    assert ((got.float() - want.float()).abs() <= 2 ** -7 * want.float().abs().clamp(min=2 ** -6)).all()
     xf = x.float() - (torch.tensor(mean, device=cuda) if mean else 0.0)
     ref = ref_conv(xf.to(torch.bfloat16), w.to(torch.bfloat16), b, True)
     assert ((got.float() - ref).abs() <= 2 ** -7 * ref.abs().clamp(min=1.0)).all()
