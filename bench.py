@@ -199,7 +199,7 @@ def run_hough(args, rank, world, local):
 # labels, SURVEY finding 10), synthetic uint8 images.
 # ------------------------------------------------------------------------------------------
 VGG_FLOP_PER_FRAME = 187.918e9  # sum of 2*M*K*N over conv1_1..conv5_3
-LAUNCHES_FULL = 14 + 6 + 7 + 2   # trunk (conv1 fused, 12 conv of which 3 with fused pool, pool4) + heads (4 conv, lowres, up8) + hough (7) + roi_pool (2)
+LAUNCHES_FULL = 14 + 6 + 7 + 2 + 1   # trunk (conv1 fused, 12 conv of which 3 with fused pool, pool4) + heads (4 conv, lowres, up8) + hough (7) + roi_pool (2) + nms_pose (1); cuBLAS fc6-8 and torch glue not counted
 
 
 def run_full(args, rank, world, local):
@@ -223,7 +223,7 @@ def run_full(args, rank, world, local):
 
     def step(img):
         L = fwd(img) if fwd is not None else net.forward(img, meta, ext, sync_rois=False)
-        rec = parallel.pack_records(L, C, rank, B)
+        rec = parallel.pack_detections(L, rank, B)     # post-NMS [roi | pose | valid] rows: the final payload
         return parallel.all_gather_records(rec, world), L
 
     sampler = ClockSampler(local)
@@ -328,10 +328,10 @@ def run_full(args, rank, world, local):
                                            "un-calibrated random init labels ~100%% of pixels foreground" % bg_shift),
         clocks=clocks, gpu_launches=LAUNCHES_FULL * args.steps,
         roofline=dict(bound="tensor", achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf, traffic=None,
-                      peak_source=peaks["source"] + " (sustained bf16 cuBLAS)", kernel="k_conv_tc<64|128|256> x13 (+im2col, 4 max-pool)",
+                      peak_source=peaks["source"] + " (sustained bf16 cuBLAS)", kernel="conv trunk: k_conv1_tc, k_conv_row2 x3, k_conv_tc<256> x9, 1 max-pool (3 pools fused)",
                       ms_per_launch_group=trunk_ms,
-                      note="achieved = 187.918 GFLOP/frame x batch / device time of the conv trunk (13 tcgen05 launches + im2col + "
-                           "4 max-pools), CUDA events; BF16 operands, FP32 accumulation"),
+                      note="achieved = 187.918 GFLOP/frame x batch / device time of the conv trunk (13 tcgen05 launches, im2col and three of "
+                           "the four max-pools fused into them), CUDA events; BF16 operands, FP32 accumulation"),
         roofline_hough=dict(bound="hbm", achieved=hough_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=hough_gbs / peaks["hbm_gbs"],
                             ms=hough_ms, note="op-boundary footprint 82.33 MB/frame / whole-op device time on the network's own "
                                               "label and vertex maps (random-init weights give unrealistic label maps; the "

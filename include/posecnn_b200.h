@@ -191,6 +191,22 @@ int pcnn_up8_heads(const float* lowres, const float* bias_score, const float* bi
 /* depthwise bilinear conv2d_transpose (k x k, stride s, SAME) on f32 NHWC — un-fused reference path */
 int pcnn_deconv_bilinear(const float* in, float* out, int B, int h, int w, int C, int k, int s, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Test-time post-processing on the device — replaces lib/utils/nms.py:3-32
+ * `nms(rois, 0.5)` and the pose assembly loop of lib/fcn/test.py:197-211:
+ *   greedy NMS in descending score order (ties: larger row index first = stable argsort reversed); a box is dropped
+ *   when IoU(+1 convention, fp32) > thresh with a kept box of the same class (per_image = 1: and the same image; the
+ *   reference ignores the batch column and only runs batch 1, per_image = 0 reproduces that);
+ *   out_rois[k] = rois[keep[k]], out_poses[k] = [poses_pred[keep[k], 4c:4c+4] | poses_init[keep[k], 4:7]].
+ * rois [capacity,7], poses_init [capacity,7], poses_pred [capacity,4C] or NULL (then poses_init is passed through);
+ * rows considered: max(*num_rois_dev, 1) when num_rois_dev != NULL (Hough's device row count; the reference always has
+ * the dummy row), else num_rows.  Outputs are capacity buffers (rows beyond *num_keep are zero, keep = -1): no host
+ * synchronisation, CUDA-graph capturable.  capacity <= PCNN_HOUGH_MAX_ROWS.
+ */
+int pcnn_nms_pose_fwd(const float* rois, const float* poses_init, const float* poses_pred, const int* num_rois_dev,
+                      int num_rows, int capacity, int num_classes, float thresh, int per_image, int32_t* keep,
+                      float* out_rois, float* out_poses, int32_t* num_keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

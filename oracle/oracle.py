@@ -161,3 +161,50 @@ def average_distance_loss(pred, target, weight, point, symmetry, margin):
     lib().pcnn_oracle_average_distance(_p(pred), _p(target), _p(weight), _p(point), _p(symmetry), N, C, P,
                                        ctypes.c_float(margin), ctypes.byref(loss), _p(diff), ctypes.byref(near))
     return np.array([loss.value], np.float32), diff
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Test-time post-processing, numpy restatement
+# ---------------------------------------------------------------------------------------------------------------
+def nms(dets, thresh, per_image=False):
+    """lib/utils/nms.py:3-32 restated: greedy NMS in descending score order over rows
+    [batch, cls, x1, y1, x2, y2, score]; a later box is dropped when IoU(+1 convention) > thresh with a kept box of the
+    same class.  float32 arithmetic as numpy does on float32 rows.  Canonical tie order: stable ascending argsort,
+    reversed (the reference's default-kind argsort()[::-1] is not stable for n > 16).  per_image=True additionally
+    requires the same batch index (the reference ignores the batch column; it only ever runs batch 1)."""
+    dets = np.asarray(dets, dtype=np.float32)
+    if dets.shape[0] == 0:
+        return []
+    cls, x1, y1, x2, y2, scores = (dets[:, k] for k in (1, 2, 3, 4, 5, 6))
+    img = dets[:, 0].astype(np.int64)
+    areas = (x2 - x1 + np.float32(1)) * (y2 - y1 + np.float32(1))        # nms.py:12
+    order = scores.argsort(kind="stable")[::-1]                           # nms.py:13 (canonical tie order)
+    keep = []
+    while order.size > 0:                                                 # nms.py:16-30
+        i = order[0]
+        keep.append(int(i))
+        rest = order[1:]
+        xx1 = np.maximum(x1[i], x1[rest]); yy1 = np.maximum(y1[i], y1[rest])
+        xx2 = np.minimum(x2[i], x2[rest]); yy2 = np.minimum(y2[i], y2[rest])
+        w = np.maximum(np.float32(0), xx2 - xx1 + np.float32(1))
+        h = np.maximum(np.float32(0), yy2 - yy1 + np.float32(1))
+        inter = w * h
+        ovr = inter / (areas[i] + areas[rest] - inter)
+        same = cls[rest] == cls[i]
+        if per_image:
+            same &= img[rest] == img[i]
+        order = rest[~((ovr > np.float32(thresh)) & same)]
+    return keep
+
+
+def assemble_poses(rois, poses_init, poses_pred, keep):
+    """lib/fcn/test.py:197-211: rows [keep]; poses[i, :4] = poses_pred[i, 4c:4c+4] for class c = rois[i, 1] >= 0."""
+    rois = np.asarray(rois, np.float32)[keep]
+    poses = np.array(np.asarray(poses_init, np.float32)[keep], copy=True)
+    if poses_pred is not None:
+        pp = np.asarray(poses_pred, np.float32)[keep]
+        for i in range(rois.shape[0]):
+            c = int(rois[i, 1])
+            if c >= 0:
+                poses[i, :4] = pp[i, 4 * c:4 * c + 4]
+    return rois, poses

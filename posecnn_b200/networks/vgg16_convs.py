@@ -23,6 +23,7 @@ from .. import conv
 from .._lib import check, lib, ptr, stream
 from ..hough_voting_gpu_layer import hough_voting_gpu_op
 from ..roi_pooling_layer import roi_pooling_op
+from ..utils import nms as dev_nms
 
 PIXEL_MEANS = (102.9801, 115.9465, 122.7717)  # lib/fcn/config.py:242 (BGR)
 
@@ -52,6 +53,7 @@ class vgg16_convs:
         self.skip_pixels = 10
         self.vote_threshold = vote_threshold
         self.vote_percentage = 0.02
+        self.nms_thresh = 0.5                      # lib/fcn/test.py:198
         self.device = torch.device(device)
         self.params: dict[str, torch.Tensor] = {}
         self._tc: dict[str, torch.Tensor] = {}
@@ -252,6 +254,11 @@ class vgg16_convs:
             x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], T["fc7/biases"]))
             x = torch.nn.functional.linear(x, T["fc8/weights"], T["fc8/biases"]).float()
             L["poses_tanh"] = torch.tanh(x)
+        if not self.is_train:
+            # test-time post-processing on the device: per-class NMS + pose assembly (lib/utils/nms.py, test.py:197-211)
+            keep, d_rois, d_poses, d_n = dev_nms.nms_pose_capacity(rois, L["poses_init"], L.get("poses_tanh"), num_rois,
+                                                                   self.nms_thresh, per_image=True, num_classes=C)
+            L["detections_keep"], L["detections_rois"], L["detections_poses"], L["num_detections"] = keep, d_rois, d_poses, d_n
         if sync_rois:
             n = max(1, int(num_rois.item()))  # the one host read the op's data-dependent shape requires
             L["rois"] = rois[:n]

@@ -50,3 +50,25 @@ def avgdist_inputs():
     q = np.array([0.8, 0.2, -0.4, 0.4], np.float32); p = q + np.array([0.1, -0.05, 0.02, 0.07], np.float32)
     targ[0, 64:68] = q / np.linalg.norm(q); pred[0, 64:68] = p / np.linalg.norm(p); wt[0, 64:68] = 1
     return pred, targ, wt, pts, synth.LOV_SYMMETRY.copy()
+
+
+def nms_inputs(seed=77, n=96, num_classes=22, batch=1):
+    """Hough-style ROI rows [batch, cls, x1, y1, x2, y2, score] with many same-class overlaps and DISTINCT scores (the
+    reference's argsort tie order is numpy-version dependent), + poses_init [n,7] and poses_pred [n,4C]."""
+    rng = np.random.default_rng(seed)
+    cls = rng.integers(1, 6, size=n)                      # few classes -> same-class overlaps are common
+    cx = rng.uniform(100, 540, size=n); cy = rng.uniform(80, 400, size=n)
+    # cluster boxes around a few centres per class so that IoU > 0.5 happens often
+    anchor = rng.integers(0, 12, size=n)
+    acx = rng.uniform(120, 520, size=12); acy = rng.uniform(100, 380, size=12)
+    near = rng.random(n) < 0.7
+    cx = np.where(near, acx[anchor] + rng.normal(0, 12, n), cx); cy = np.where(near, acy[anchor] + rng.normal(0, 12, n), cy)
+    w = rng.uniform(60, 160, size=n); h = rng.uniform(60, 160, size=n)
+    rois = np.zeros((n, 7), np.float32)
+    rois[:, 0] = rng.integers(0, batch, size=n)
+    rois[:, 1] = cls
+    rois[:, 2] = cx - w / 2; rois[:, 3] = cy - h / 2; rois[:, 4] = cx + w / 2; rois[:, 5] = cy + h / 2
+    rois[:, 6] = rng.permutation(n).astype(np.float32) * 7 + 500       # distinct integer-valued vote counts
+    poses_init = rng.standard_normal((n, 7)).astype(np.float32)
+    poses_pred = np.tanh(rng.standard_normal((n, 4 * num_classes))).astype(np.float32)
+    return rois, poses_init, poses_pred

@@ -32,7 +32,13 @@ def _worker(rank, world, port, out_dir):
     L = _fake_layers(rank, C, cap, n_valid=5 + 3 * rank)
     rec = parallel.pack_records(L, C, rank, local_batch)
     allrec = parallel.all_gather_records(rec, world)
-    torch.save(dict(rec=rec, allrec=allrec), os.path.join(out_dir, f"r{rank}.pt"))
+    # post-NMS detections (final payload) and the training-side loss normaliser
+    nd = 2 + rank
+    L.update(detections_rois=L["rois_capacity"].clone(), detections_poses=L["poses_init"].clone(),
+             num_detections=torch.tensor([nd], dtype=torch.int32))
+    det = parallel.all_gather_records(parallel.pack_detections(L, rank, local_batch), world)
+    loss, gscale = parallel.global_mean_loss(torch.tensor(1.0 + rank), 3 + 5 * rank, world)
+    torch.save(dict(rec=rec, allrec=allrec, det=det, loss=loss, gscale=gscale), os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,6 +61,14 @@ def test_all_gather_records_gloo_world2(tmp_path):
         np.testing.assert_array_equal(blk[:n_valid, 0].numpy(), (L["rois_capacity"][:n_valid, 0] + r * local_batch).numpy())
         assert torch.equal(blk[:n_valid, 1:7], L["rois_capacity"][:n_valid, 1:7])
         assert torch.equal(blk[:n_valid, 14:14 + 4 * C], L["poses_tanh"][:n_valid])
+        det = outs[0]["det"][r * cap:(r + 1) * cap]
+        assert det.shape[1] == parallel.detection_width() and det[:, -1].sum().item() == 2 + r and not det[2 + r:].any()
+        assert torch.equal(det[:2 + r, 7:14], L["poses_init"][:2 + r])
+        np.testing.assert_array_equal(det[:2 + r, 0].numpy(), (L["rois_capacity"][:2 + r, 0] + r * local_batch).numpy())
+    assert torch.equal(outs[0]["det"], outs[1]["det"])
+    # ranks hold means 1.0 (3 rows) and 2.0 (8 rows): global mean = (3 + 16) / 11; grad scales N_r * world / N
+    assert abs(outs[0]["loss"].item() - 19.0 / 11.0) < 1e-6 and abs(outs[1]["loss"].item() - 19.0 / 11.0) < 1e-6
+    assert abs(outs[0]["gscale"].item() - 6.0 / 11.0) < 1e-6 and abs(outs[1]["gscale"].item() - 16.0 / 11.0) < 1e-6
 
 
 def test_pack_records_single_process():
