@@ -453,7 +453,10 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
             uint32_t pa = 0, pb = 0;
             if (RESB) {
                 mbar_arrive_expect_tx(wbar, 9 * Plan::kBBytes);
-                for (int tap = 0; tap < 9; tap++) tma_load_2d(sB + tap * Plan::kBBytes, &map_w, wbar, tap * p.Cin, nt_fixed * BN);
+                // resident slices in (s, r) order: the slices of taps (r - 1, s) and (r, s) are adjacent and form ONE
+                // 128-row B tile for the merged two-row MMA below
+                for (int tap = 0; tap < 9; tap++)
+                    tma_load_2d(sB + ((tap % 3) * 3 + tap / 3) * Plan::kBBytes, &map_w, wbar, tap * p.Cin, nt_fixed * BN);
             }
             for (int tile = tile0; tile < tcount; tile += tstep) {
                 const int nt = RESB ? nt_fixed : tile % p.n_tiles_n;
@@ -494,7 +497,38 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
                 for (int c = 0; c < kchunks; c++) {
                     mbar_wait(&fullA[sa], pa);
                     const uint32_t a_base = smem_u32(smem + sa * kPatchBytes);
-                    for (int tap = 0; tap < 9; tap++) {
+                    if (RESB) {
+                        // The A operand of tap (r, s) for output row j is patch row rho = r + j: rows 0 and 1 of the pair
+                        // read the SAME A tile for rho = 1, 2 (taps r = rho and r = rho - 1).  One N = 2 BN MMA against
+                        // the two adjacent weight slices [W(rho-1, s) | W(rho, s)] writes [acc(row 1) | acc(row 0)]:
+                        // A is fetched once instead of twice (with N = 64 the MMA is bound by the 128 B/clk shared-memory
+                        // operand fetch, ncu: 65 clk per MMA for 33 clk of math).  rho = 1 goes first so that the first
+                        // MMA initialises both accumulators.
+                        tc_fence_after();
+                        constexpr uint32_t idesc2 = make_idesc(2 * BN);
+                        const uint32_t d_pair = tmem_base + (acc * 2) * BN;      // [row 1 | row 0]
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            const int rho = o == 0 ? 1 : (o == 1 ? 2 : (o == 2 ? 0 : 3));
+#pragma unroll
+                            for (int s3 = 0; s3 < 3; s3++) {
+                                const uint64_t da = make_desc(a_base + (uint32_t)((rho * kPatchW + s3) * 128));
+                                if (rho == 1 || rho == 2) {
+                                    const uint64_t db = make_desc(smem_u32(sB + (s3 * 3 + rho - 1) * Plan::kBBytes));
+#pragma unroll
+                                    for (int k = 0; k < kKC / 16; k++)
+                                        umma_bf16(d_pair, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (c | o | s3 | k) != 0);
+                                } else {
+                                    // rho = 0: row 0 only, tap r = 0;  rho = 3: row 1 only, tap r = 2
+                                    const uint64_t db = make_desc(smem_u32(sB + (s3 * 3 + (rho == 0 ? 0 : 2)) * Plan::kBBytes));
+                                    const uint32_t d1 = d_pair + (rho == 0 ? BN : 0);
+#pragma unroll
+                                    for (int k = 0; k < kKC / 16; k++) umma_bf16(d1, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);
+                                }
+                            }
+                        }
+                    }
+                    for (int tap = 0; tap < (RESB ? 0 : 9); tap++) {
                         if (!RESB) mbar_wait(&fullB[sb], pb);
                         tc_fence_after();
                         const int r = tap / 3, s = tap - 3 * r;
@@ -544,7 +578,7 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
                         uint32_t rr[32];
-                        tmem_ld_32x32(t_lane + (acc * 2 + j) * BN + g * 64 + half * 32, rr);
+                        tmem_ld_32x32(t_lane + (acc * 2 + (RESB ? 1 - j : j)) * BN + g * 64 + half * 32, rr);   // RESB: [row 1 | row 0]
                         tmem_ld_wait();
                         const float* bias = p.bias + n0 + g * 64 + half * 32;
 #pragma unroll

@@ -119,13 +119,13 @@ def test_conv_row_mode(cuda, B, H, W, Cin, Cout):
     torch.cuda.synchronize()
     want = ref_conv(x, wf, bias, True)
     assert ((row.float() - want).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()
-    if Cin == 64:
+    if Cin == 64 and Cout == 128:
         assert torch.equal(row, tile)            # same accumulation order -> bit identical
-    else:                                        # chunk-outer vs tap-outer accumulation order: fp32 rounding only
-        assert ((row.float() - tile.float()).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()
+    else:                                        # chunk-outer (Cin = 128) or patch-row-outer (merged two-row MMAs, Cout = 64)
+        assert ((row.float() - tile.float()).abs() <= 2 ** -7 * want.abs().clamp(min=1.0)).all()    # order: fp32 rounding only
     rowp = conv.conv_pool_bf16(x, w, bias, 3, True, 0)
     tilep = conv.conv_pool_bf16(x, w, bias, 3, True, Cout)
     torch.cuda.synchronize()
     assert torch.equal(rowp, conv.maxpool2x2(row))
-    if Cin == 64:
+    if Cin == 64 and Cout == 128:
         assert torch.equal(rowp, tilep)
