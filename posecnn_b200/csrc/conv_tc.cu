@@ -671,10 +671,12 @@ k_conv_row2(const __grid_constant__ CUtensorMap map_in /*box {64,130,4,1}*/, con
 // epilogues in flight per SM (ncu on the 2-builder / 1-epilogue version: issue slots 44 % busy, 0.9 us per tile).
 // ---------------------------------------------------------------------------------------------
 constexpr int kC1Stages = 6;
-constexpr int kC1EpiGroups = 2, kC1BuildGroups = 4;
+constexpr int kC1EpiGroups = 2, kC1BuildGroups = 4, kC1Accs = 4;
 constexpr int kC1Threads = 128 * (kC1EpiGroups + kC1BuildGroups) + 32;  // 8 epilogue warps, 16 A-builder warps, 1 MMA warp
 constexpr int kC1MmaWarp = 4 * (kC1EpiGroups + kC1BuildGroups);
-constexpr int kC1BarOff = kC1Stages * kABytes + 64 * 128 + kC1EpiGroups * 2 * kStageBytes;
+constexpr int kC1PatchWords = 10 * 16;   // raw uint8 input patch of a tile: 10 rows x 14 words (+2 pad), per builder group x 2 buffers
+constexpr int kC1PatchOff = kC1Stages * kABytes + 64 * 128 + kC1EpiGroups * 2 * kStageBytes;
+constexpr int kC1BarOff = kC1PatchOff + kC1BuildGroups * 2 * kC1PatchWords * 4;
 constexpr int kC1Smem = kC1BarOff + 256 + 1024;
 
 template <typename TIn>
@@ -690,17 +692,17 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kC1BarOff);
     uint64_t* empty = full + kC1Stages;
     uint64_t* tfull = empty + kC1Stages;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* wbar = tempty + 2;
+    uint64_t* tempty = tfull + kC1Accs;
+    uint64_t* wbar = tempty + kC1Accs;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wbar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kTmemCols = kC1Accs * BN;
 
     if (warp == kC1MmaWarp && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         for (int s = 0; s < kC1Stages; s++) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < kC1Accs; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
@@ -715,7 +717,10 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
         const int group = (threadIdx.x - 128 * kC1EpiGroups) >> 7;
         const int r = (threadIdx.x - 128 * kC1EpiGroups) & 127;
         const int hl = r >> 4, wl = r & 15;
-        int it = 0;
+        uint32_t* patch_base = reinterpret_cast<uint32_t*>(smem + kC1PatchOff);
+        // aligned-word staging needs word-aligned image rows
+        const bool fast_u8 = sizeof(TIn) == 1 && (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0;
+        int it = 0, lit = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
             if (it % kC1BuildGroups != group) continue;
             const int stage = it % kC1Stages;
@@ -731,18 +736,74 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             v[27] = 1.f; v[28] = 1.f;
 #pragma unroll
             for (int k = 29; k < 32; k++) v[k] = 0.f;
+            bool done = false;
+            if constexpr (sizeof(TIn) == 1) {
+                if (fast_u8) {
+                    // uint8 fast path: the tile's raw 10 x 18 px patch is staged once in shared memory with aligned
+                    // 32-bit loads -- a patch row starts at byte (16 tw - 1) * 3 = 48 tw - 3 of the image row, so the
+                    // 14-word window from byte 48 tw - 4 is word aligned and the patch sits at byte offset 1 in it --
+                    // and every thread then cuts its 3 x 9 bytes out of it (3 words + 2 byte-permutes per row) instead
+                    // of issuing 27 byte loads with their own address arithmetic and bounds tests.
+                    uint32_t* pw = patch_base + (group * 2 + (lit & 1)) * kC1PatchWords;
+                    const int y0 = th * kTileH - 1, wq0 = 12 * tw - 1, row_words = (p.W * 3) >> 2;
+                    const uint32_t* img32 = reinterpret_cast<const uint32_t*>(base);
+                    for (int idx = r; idx < 140; idx += 128) {
+                        const int prow = idx / 14, wi = idx - prow * 14;
+                        const int yy = y0 + prow, wq = wq0 + wi;
+                        uint32_t word = 0;
+                        if (yy >= 0 && yy < p.H && wq >= 0 && wq < row_words) word = __ldg(img32 + (size_t)yy * row_words + wq);
+                        pw[prow * 16 + wi] = word;
+                    }
+                    if (group == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+                    else if (group == 1) asm volatile("bar.sync 4, 128;" ::: "memory");
+                    else if (group == 2) asm volatile("bar.sync 5, 128;" ::: "memory");
+                    else asm volatile("bar.sync 6, 128;" ::: "memory");
+                    const int boff = 1 + 3 * wl, w0 = boff >> 2, o = boff & 3;
+                    const uint32_t sel = (uint32_t)(o | ((o + 1) << 4) | ((o + 2) << 8) | ((o + 3) << 12));
+                    const bool border = th == 0 || th * kTileH + kTileH + 1 > p.H || tw == 0 || tw * kTileW + kTileW + 1 > p.W;
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++) {
-                const int yy = y + dy - 1;
-                const bool rowok = yy >= 0 && yy < p.H;
+                    for (int dy = 0; dy < 3; dy++) {
+                        const uint32_t* rowp = pw + (hl + dy) * 16 + w0;
+                        const uint32_t a0 = rowp[0], a1 = rowp[1], a2 = rowp[2];
+                        const uint32_t b03 = __byte_perm(a0, a1, sel), b47 = __byte_perm(a1, a2, sel), b8 = (a2 >> (8 * o)) & 0xffu;
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    const int xx = x + dx - 1;
-                    const bool ok = rowok && xx >= 0 && xx < p.W;
-                    const TIn* px = base + ((size_t)yy * p.W + xx) * 3;
-                    v[(dy * 3 + dx) * 3 + 0] = ok ? (float)px[0] - m0 : 0.f;
-                    v[(dy * 3 + dx) * 3 + 1] = ok ? (float)px[1] - m1 : 0.f;
-                    v[(dy * 3 + dx) * 3 + 2] = ok ? (float)px[2] - m2 : 0.f;
+                        for (int k = 0; k < 9; k++) {
+                            const uint32_t byte = k < 4 ? (b03 >> (8 * k)) & 0xffu : (k < 8 ? (b47 >> (8 * (k - 4))) & 0xffu : b8);
+                            const int c = k % 3;
+                            v[dy * 9 + k] = (float)byte - (c == 0 ? m0 : (c == 1 ? m1 : m2));
+                        }
+                    }
+                    if (border) {   // SAME padding pads the mean-subtracted image with zeros
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            const int yy = y + dy - 1;
+#pragma unroll
+                            for (int dx = 0; dx < 3; dx++) {
+                                const int xx = x + dx - 1;
+                                if (!(yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)) {
+                                    v[(dy * 3 + dx) * 3 + 0] = 0.f; v[(dy * 3 + dx) * 3 + 1] = 0.f; v[(dy * 3 + dx) * 3 + 2] = 0.f;
+                                }
+                            }
+                        }
+                    }
+                    lit++;
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++) {
+                    const int yy = y + dy - 1;
+                    const bool rowok = yy >= 0 && yy < p.H;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        const int xx = x + dx - 1;
+                        const bool ok = rowok && xx >= 0 && xx < p.W;
+                        const TIn* px = base + ((size_t)yy * p.W + xx) * 3;
+                        v[(dy * 3 + dx) * 3 + 0] = ok ? (float)px[0] - m0 : 0.f;
+                        v[(dy * 3 + dx) * 3 + 1] = ok ? (float)px[1] - m1 : 0.f;
+                        v[(dy * 3 + dx) * 3 + 2] = ok ? (float)px[2] - m2 : 0.f;
+                    }
                 }
             }
             mbar_wait(&empty[stage], phase ^ 1);
@@ -789,15 +850,16 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int acc = it % kC1Accs;
+                const uint32_t acc_phase = (it / kC1Accs) & 1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint64_t da = make_desc(smem_u32(smem + stage * kABytes));
                 umma_bf16(tmem_base + acc * BN, da, db, idesc, 0);            // K 0..15
                 umma_bf16(tmem_base + acc * BN, da + 2, db + 2, idesc, 1);    // K 16..31 (27..31 are zero)
-                umma_commit(&empty[stage]);
+                // ONE commit per tile: the epilogue that observes tfull also releases the A stage (software arrive on
+                // empty[stage]) -- a second tcgen05.commit per 2-MMA tile costs more than the tile's math
                 umma_commit(&tfull[acc]);
                 if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
             }
@@ -814,28 +876,34 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
             const int tw = tile % p.tiles_w;
             const int rest = tile / p.tiles_w;
             const int th = rest % p.tiles_h, img = rest / p.tiles_h;
-            const int acc = eg;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int acc = it % kC1Accs;                 // four TMEM accumulators: the MMA warp runs up to four tiles ahead
+            const uint32_t acc_phase = (it / kC1Accs) & 1;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (wq == 0 && lane == 0) mbar_arrive(&empty[it % kC1Stages]);   // the tile's MMAs are done reading its A stage
             const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BN;
-            if (issuer) tma_store_wait_read<1>();
+            // both halves of the accumulator into registers, then hand the TMEM stage back before any math
+            uint32_t rr[2][32];
+            tmem_ld_32x32(t_addr, rr[0]);
+            tmem_ld_32x32(t_addr + 32, rr[1]);
+            if (issuer) tma_store_wait_read<1>();         // overlaps the TMEM read latency
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
             else asm volatile("bar.sync 2, 128;" ::: "memory");
             uint8_t* ob = my_stage + obuf * kStageBytes;
+            const __nv_bfloat162 floor2 = __floats2bfloat162_rn(p.relu ? 0.f : -INFINITY, p.relu ? 0.f : -INFINITY);
 #pragma unroll
             for (int half = 0; half < 2; half++) {
-                uint32_t rr[32];
-                tmem_ld_32x32(t_addr + half * 32, rr);
-                tmem_ld_wait();
-                const __nv_bfloat162 floor2 = __floats2bfloat162_rn(p.relu ? 0.f : -INFINITY, p.relu ? 0.f : -INFINITY);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     uint32_t packed[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         // bias already inside the accumulator; ReLU on the packed pair (rounding is monotone, 0 is exact)
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(rr[j * 8 + q * 2]), __uint_as_float(rr[j * 8 + q * 2 + 1]));
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(rr[half][j * 8 + q * 2]), __uint_as_float(rr[half][j * 8 + q * 2 + 1]));
                         b2 = __hmax2(b2, floor2);
                         packed[q] = *reinterpret_cast<uint32_t*>(&b2);
                     }
@@ -843,9 +911,6 @@ k_conv1_tc(const TIn* __restrict__ in, const __grid_constant__ CUtensorMap map_w
                     *reinterpret_cast<uint4*>(ob + row * 128 + ((piece ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
             fence_proxy_async();
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
             else asm volatile("bar.sync 2, 128;" ::: "memory");
