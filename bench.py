@@ -327,7 +327,7 @@ def run_full(args, rank, world, local):
                     background_calibration="score/biases[0] += %.4g so that ~75%% of pixels are background (YCB-like fill); "
                                            "un-calibrated random init labels ~100%% of pixels foreground" % bg_shift),
         clocks=clocks, gpu_launches=LAUNCHES_FULL * args.steps,
-        roofline=dict(bound="tensor", achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf, traffic=None,
+        roofline=dict(bound="tensor", achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf, traffic=trunk_traffic(B),
                       peak_source=peaks["source"] + " (sustained bf16 cuBLAS)", kernel="conv trunk: k_conv1_tc, k_conv_row2 x3, k_conv_tc<256> x9, 1 max-pool (3 pools fused)",
                       ms_per_launch_group=trunk_ms,
                       note="achieved = 187.918 GFLOP/frame x batch / device time of the conv trunk (13 tcgen05 launches, im2col and three of "
@@ -359,7 +359,17 @@ def max_over_ranks(x, world):
     return float(x)
 
 
-def cpu_baseline(sample_frames=2):
+def trunk_traffic(batch):
+    """DRAM bytes of the conv trunk per launch group from the committed ncu capture (profiles/step_breakdown.py)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_full_b32_trunk_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d["trunk_dram_bytes_per_launch_group"] if d.get("batch") == batch else None
+    except Exception:
+        return None
+
+
+def cpu_baseline(sample_frames=32):
     """Reference CPU hough_voting_layer (RANSAC) restated in C++ (oracle/cpu_hough_ransac.cpp), timed on host cores."""
     try:
         from oracle import cpu_hough

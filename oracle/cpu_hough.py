@@ -44,38 +44,80 @@ def hough_voting(label, vertex, extents, meta, is_train=0, threads=1):
 
 
 def _bench_frames(nframes, seed0=2234):
+    """Same generator and shapes as the GPU workload, with ONE change: the CPU op reads the third vertex channel as a
+    metric distance and REJECTS samples whose value is negative (samplePoint2D, hough_voting_op.cc:338-352; no exp,
+    unlike the GPU op), so with log-depth targets every object nearer than 1 m sends its hypothesis loop into the
+    10^7-iteration rejection limit (measured: 14 s for one frame).  The baseline frames therefore carry z instead of
+    log z in that channel -- the op's own convention -- so that the timing measures RANSAC, not the rejection loop."""
     from posecnn_b200 import synth
-    return synth.make_scene(batch=nframes, height=480, width=640, num_classes=22, seed=seed0)
+    sc = synth.make_scene(batch=nframes, height=480, width=640, num_classes=22, seed=seed0)
+    sc["vertex"][..., 2::3] = np.exp(sc["vertex"][..., 2::3])
+    return sc
 
 
-def timed_baseline(sample_frames=2, threads=None, repeats=3):
-    """frames/s of the CPU op on `sample_frames` synthetic 640x480 / 22-class frames (same generator and
-    shapes as the GPU workload); best-effort variant: all host cores (OpenMP on), -O3."""
-    cores = threads or os.cpu_count() or 1
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _best_threads(probe_args, limit=None):
+    """The op's OpenMP regions are short (per class, per RANSAC round): more threads are not always faster and on a
+    128-thread host the all-cores run is ~60x SLOWER than one thread.  "All the host threads it can use" is therefore
+    decided by measurement: time a 2-frame probe at 1, 2, 4, ... , all cores and keep the fastest."""
+    n = limit or _host_cores()
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, n) if c <= n})
+    timing = {}
+    for c in cands:
+        hough_voting(*probe_args, threads=c)                     # warm the thread pool
+        best_t = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            hough_voting(*probe_args, threads=c)
+            best_t = min(best_t, time.perf_counter() - t0)
+        timing[c] = best_t
+        if timing[c] > 4 * min(timing.values()) and c >= 8:      # clearly past the optimum: stop climbing
+            break
+    best = min(timing, key=timing.get)
+    return best, {c: round(1e3 * t, 2) for c, t in timing.items()}
+
+
+def timed_baseline(sample_frames=32, threads=None, repeats=5):
+    """frames/s of the CPU op on `sample_frames` synthetic 640x480 / 22-class frames (same generator and shapes as the
+    GPU workload); best-effort variant: -O3, OpenMP on, thread count = the fastest of a measured sweep (see
+    _best_threads); the as-shipped single-thread figure is reported beside it."""
+    probe = _bench_frames(2)
+    pa = (probe["label"], probe["vertex"], probe["extents"], probe["meta"])
+    sweep = None
+    if threads is None:
+        threads, sweep = _best_threads(pa)
     sc = _bench_frames(sample_frames)
     args = (sc["label"], sc["vertex"], sc["extents"], sc["meta"])
-    hough_voting(*args, threads=cores)  # warm-up
+    hough_voting(*args, threads=threads)  # warm-up
     ts = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        hough_voting(*args, threads=cores)
+        hough_voting(*args, threads=threads)
         ts.append(time.perf_counter() - t0)
-    t1 = []
     t0 = time.perf_counter()
-    hough_voting(*args, threads=1)
-    t1 = time.perf_counter() - t0
+    hough_voting(*pa, threads=1)
+    t1 = (time.perf_counter() - t0) / 2
     dt = float(np.median(ts))
-    return dict(value=sample_frames / dt, unit="frames/s", cores=cores, kind="port",
-                sample=f"{sample_frames} synthetic 640x480x22-class frames, CPU hough_voting_layer (RANSAC) restated in C++ "
-                       f"(-O3 -fopenmp, {cores} threads; as-shipped 1-thread: {sample_frames / t1:.2f} frames/s), "
-                       f"median of {repeats}", ms_per_frame=1e3 * dt / sample_frames,
-                single_thread_frames_per_s=sample_frames / t1)
+    return dict(value=sample_frames / dt, unit="frames/s", cores=threads, kind="port",
+                sample=f"{sample_frames} synthetic 640x480x22-class frames x {repeats} runs, CPU hough_voting_layer (RANSAC) "
+                       f"restated in C++ (-O3 -fopenmp); {threads} threads = fastest of the sweep {sweep} (ms per 2-frame probe) "
+                       f"on {_host_cores()} host cores; as-shipped 1-thread: {1.0 / t1:.2f} frames/s",
+                ms_per_frame=1e3 * dt / sample_frames, single_thread_frames_per_s=1.0 / t1, host_cores=_host_cores(),
+                thread_sweep_ms=sweep)
 
 
 def reference_arm(args):
-    """`bench.py --impl reference`: the reference's own CPU implementation of the path on host cores."""
-    cores = os.cpu_count() or 1
-    frames = 2
+    """`bench.py --impl reference`: the reference's own CPU implementation of the path on host cores (thread count =
+    the fastest of a measured sweep; all cores is far from the fastest for this op)."""
+    frames = 32
+    probe = _bench_frames(2)
+    cores, sweep = _best_threads((probe["label"], probe["vertex"], probe["extents"], probe["meta"]))
     sc = _bench_frames(frames)
     a = (sc["label"], sc["vertex"], sc["extents"], sc["meta"])
     for _ in range(max(1, min(args.warmup, 2))):
@@ -89,6 +131,7 @@ def reference_arm(args):
                 n_gpus=0, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64/f32", data="synthetic",
                 config=dict(workload=f"CPU hough_voting_layer (RANSAC), {frames} frames 640x480x22 per step"),
-                cpu_baseline=dict(value=v, unit="frames/s", cores=cores, kind="port",
-                                  sample=f"{frames} frames per step, {args.steps} steps, {cores} OpenMP threads"),
+                cpu_baseline=dict(value=v, unit="frames/s", cores=cores, kind="port", host_cores=_host_cores(),
+                                  sample=f"{frames} frames per step, {args.steps} steps, {cores} OpenMP threads (fastest of sweep "
+                                         f"{sweep} ms per 2-frame probe)"),
                 e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
