@@ -81,7 +81,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = os.environ.get("PCNN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL prints its version line on stdout otherwise
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -378,7 +378,28 @@ def cpu_baseline(sample_frames=32):
     return cpu_hough.timed_baseline(sample_frames)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the result JSON: keep a private handle on the real stdout and point fd 1 at
+    stderr so that anything a library prints (NCCL's version banner, torchrun notices) cannot end up next to it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(result):
+    out = claim_stdout()
+    out.write(json.dumps(result) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -397,7 +418,7 @@ def main():
         if rank != 0:
             return
         from oracle import cpu_hough
-        print(json.dumps(cpu_hough.reference_arm(args)))
+        emit(cpu_hough.reference_arm(args))
         return
 
     rank, world, local = dist_setup(args.gpus)
@@ -405,7 +426,7 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             res["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(res))
+        emit(res)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
