@@ -1,11 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo rc=$?; wc -l gpurun_out/bench_2gpu.json; python - <<'PY'
-import json
-for l in open('gpurun_out/bench_2gpu.json'):
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'], d['config'].get('parallelism'))
-    else: print('NON-JSON LINE:', l[:200])
-PY
-tail -3 gpurun_out/bench_2gpu.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -c 600
+( timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_nms_gpu.py tests/test_pixel_ops_gpu.py tests/test_hough_gpu.py -m gpu -x -q -k "not batch32 and not full_size" 2>&1 | tail -6 ) > gpurun_out/sanitizer_ops.txt; cat gpurun_out/sanitizer_ops.txt
+( timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_network_gpu.py tests/test_conv_gpu.py -m gpu -x -q 2>&1 | tail -8 ) > gpurun_out/sanitizer_net.txt; cat gpurun_out/sanitizer_net.txt
+( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_nms_gpu.py -m gpu -x -q -k "golden or ties" 2>&1 | tail -5 ) > gpurun_out/sanitizer_race_nms.txt; cat gpurun_out/sanitizer_race_nms.txt
