@@ -174,42 +174,72 @@ k_roi_pool_fwd_bf16_s4(const __nv_bfloat16* __restrict__ bottom, const float* __
         float mv[8];
         int mi[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { mv[k] = empty ? 0.f : -FLT_MAX; mi[k] = -1; }
+        for (int k = 0; k < 8; k++) { mv[k] = 0.f; mi[k] = -1; }
         if (!empty) {
             const __nv_bfloat16* img = bottom + (size_t)rb.b * height * width * channels;
             const int bw = rb.we - rb.ws, cells = bw * (rb.he - rb.hs);
+            // Running maximum and its cell number stay PACKED: max as bf16x2 (HMNMX2), "is greater" as a 0xFFFF-per-half
+            // mask (HSET2), cell number as u16x2 merged with one LOP3 -- 3 instructions per channel pair and cell instead
+            // of 8 on unpacked floats.  Cell number = position in the bin's raster scan (< 65536: a bin has at most
+            // height * width cells, checked on the host), so "smaller cell number" == "earlier in the reference's scan".
+            // Start value -inf: every finite feature is greater, like the reference's -FLT_MAX (.cu.cc:57).
+            uint32_t m2[4], c2[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { m2[k] = 0xff80ff80u; c2[k] = 0xffffffffu; }
             for (int i0 = slice; i0 < cells; i0 += 4 * kRoiSlices) {
                 uint4 q[4];
-                int bi[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int i = i0 + u * kRoiSlices;
-                    const int ic = min(i, cells - 1);
+                    const int ic = min(i0 + u * kRoiSlices, cells - 1);
                     const int hh = ic / bw, ww = ic - hh * bw;
-                    bi[u] = i < cells ? ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0 : -1;
                     q[u] = __ldg(reinterpret_cast<const uint4*>(img + ((rb.hs + hh) * width + rb.ws + ww) * channels + ch0));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (bi[u] < 0) continue;
-                    const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+                    const int i = i0 + u * kRoiSlices;
+                    if (i >= cells) continue;
+                    const uint32_t i2 = (uint32_t)i * 0x10001u;
+                    const uint32_t* qw = reinterpret_cast<const uint32_t*>(&q[u]);
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const float2 f = __bfloat1622float2(q2[k]);
-                        if (f.x > mv[2 * k]) { mv[2 * k] = f.x; mi[2 * k] = bi[u] + 2 * k; }
-                        if (f.y > mv[2 * k + 1]) { mv[2 * k + 1] = f.y; mi[2 * k + 1] = bi[u] + 2 * k + 1; }
+                        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&qw[k]);
+                        const __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&m2[k]);
+                        const uint32_t gt = __hgt2_mask(v, m);              // strict '>' per half (.cu.cc:73)
+                        const __nv_bfloat162 nm = __hmax2(v, m);
+                        m2[k] = *reinterpret_cast<const uint32_t*>(&nm);
+                        c2[k] = (c2[k] & ~gt) | (i2 & gt);
                     }
                 }
             }
+            // merge the slices: larger value, on ties the smaller cell number (a slice without cells holds -inf / 0xffff)
 #pragma unroll
             for (int d = 4; d <= 16; d <<= 1) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, mv[k], d);
-                    const int oi = __shfl_xor_sync(0xffffffffu, mi[k], d);
-                    // a slice that saw no cell still holds (-FLT_MAX, -1): never wins against a real cell
-                    if (oi >= 0 && (ov > mv[k] || (ov == mv[k] && (mi[k] < 0 || oi < mi[k])))) { mv[k] = ov; mi[k] = oi; }
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t om = __shfl_xor_sync(0xffffffffu, m2[k], d);
+                    const uint32_t oc = __shfl_xor_sync(0xffffffffu, c2[k], d);
+                    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&m2[k]);
+                    const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(&om);
+                    const uint32_t gt = __hgt2_mask(o, a), eq = __heq2_mask(o, a);
+                    // per half: other cell number smaller?  (16-bit unsigned compare on both halves)
+                    const uint32_t lo_lt = ((oc & 0xffffu) < (c2[k] & 0xffffu)) ? 0x0000ffffu : 0u;
+                    const uint32_t hi_lt = ((oc >> 16) < (c2[k] >> 16)) ? 0xffff0000u : 0u;
+                    const uint32_t take = gt | (eq & (lo_lt | hi_lt));
+                    m2[k] = (m2[k] & ~take) | (om & take);
+                    c2[k] = (c2[k] & ~take) | (oc & take);
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&m2[k]));
+                const int i_lo = (int)(c2[k] & 0xffffu), i_hi = (int)(c2[k] >> 16);
+                // every non-empty bin has at least one cell and all features are finite -> a cell number was recorded;
+                // 0xffff survives only if the feature was -inf / NaN, reported like the reference's untouched start value
+                mv[2 * k] = i_lo == 0xffff ? -FLT_MAX : f.x;
+                mv[2 * k + 1] = i_hi == 0xffff ? -FLT_MAX : f.y;
+                const int h_lo = i_lo / bw, h_hi = i_hi / bw;
+                mi[2 * k] = i_lo == 0xffff ? -1 : ((rb.hs + h_lo) * width + rb.ws + (i_lo - h_lo * bw)) * channels + ch0 + 2 * k;
+                mi[2 * k + 1] = i_hi == 0xffff ? -1 : ((rb.hs + h_hi) * width + rb.ws + (i_hi - h_hi * bw)) * channels + ch0 + 2 * k + 1;
             }
         }
         if (slice == 0) {
@@ -769,7 +799,8 @@ extern "C" int pcnn_roi_pool_fwd_bf16(const void* bottom_bf16, const float* rois
     PCNN_REQUIRE(channel_rois >= 6 && channels % 8 == 0, "roi_pool_bf16: needs >= 6 roi columns and channels %% 8 == 0");
     if (num_rois == 0 || pooled_height == 0 || pooled_width == 0) return PCNN_OK;
     size_t total = (size_t)num_rois * pooled_height * pooled_width * (channels / 8);
-    if (channels % 32 == 0 && (long long)num_rois * pooled_height * pooled_width * (channels / 32) * 32 < 0x7fffffffLL) {
+    if (channels % 32 == 0 && height * width < 0xffff &&
+        (long long)num_rois * pooled_height * pooled_width * (channels / 32) * 32 < 0x7fffffffLL) {
         size_t threads = (size_t)num_rois * pooled_height * pooled_width * (channels / 32) * 32;
         k_roi_pool_fwd_bf16_s4<<<grid_for(threads, 256), 256, 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)bottom_bf16, rois, num_rois, channel_rois, batch, height, width, channels, pooled_height,
