@@ -207,6 +207,30 @@ int pcnn_nms_pose_fwd(const float* rois, const float* poses_init, const float* p
                       int num_rows, int capacity, int num_classes, float thresh, int per_image, int32_t* keep,
                       float* out_rois, float* out_poses, int32_t* num_keep, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training-side target generation and fused losses.
+ *  pcnn_vertex_targets_fwd     lib/gt_synthesize_layer/minibatch.py:543-602 (_generate_vertex_targets, single-instance
+ *      branch): label [B,H,W] int32, centers [B,C,3] = (cx, cy, z) of each class's projected centre (z <= 0: class
+ *      absent from the image) -> vertex_targets / vertex_weights [B,H,W,3C] f32 (zero elsewhere); float64 arithmetic
+ *      rounded to float32 like numpy's (float32 centre - int64 pixel grid).
+ *  pcnn_loss_cls_hard_fwd      lib/fcn/train.py:455-465 on the Hardlabel mask (hard_label_op_gpu.cu.cc:16-29) without
+ *      materialising it: loss = -sum_{selected p} score[p, gt_p] / (count + 1e-10), score = log-softmax [B,H,W,C];
+ *      loss_out[0] = loss, loss_out[1] = count; grad_score (optional, [B,H,W,C]) = upstream * d loss / d score.
+ *  pcnn_smooth_l1_vertex_fwd   lib/fcn/train.py:564-573: loss_out[0] = sum(in_loss) / (sum(weights) + 1e-10),
+ *      loss_out[1] = sum(weights); grad_pred optional.
+ * Both losses reduce per-CTA partial sums (double) in index order: run-to-run deterministic.  workspace: zero-filled
+ * once by the caller (pcnn_train_loss_workspace_bytes), reusable across launches on one stream.
+ */
+int pcnn_train_loss_workspace_bytes(size_t* bytes);
+int pcnn_vertex_targets_fwd(const int32_t* label, const float* centers, int B, int H, int W, int C, float w_inside,
+                            float* targets, float* weights, void* stream);
+int pcnn_loss_cls_hard_fwd(const float* score, const float* prob, const int32_t* gt, int B, int H, int W, int C,
+                           float threshold, float* loss_out, float upstream, float* grad_score, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int pcnn_smooth_l1_vertex_fwd(const float* pred, const float* targets, const float* weights, size_t n, float sigma,
+                              float* loss_out, float upstream, float* grad_pred, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -208,3 +208,51 @@ def assemble_poses(rois, poses_init, poses_pred, keep):
             if c >= 0:
                 poses[i, :4] = pp[i, 4 * c:4 * c + 4]
     return rois, poses
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training-side targets and losses, numpy restatements
+# ---------------------------------------------------------------------------------------------------------------
+def generate_vertex_targets(label, centers, w_inside):
+    """lib/gt_synthesize_layer/minibatch.py:578-599 (single-instance branch, VERTEX_REG_2D): label [B,H,W] int32,
+    centers [B,C,3] = (cx, cy, z), z <= 0 = class not in cls_indexes.  float32 centre - int64 pixel grid = float64
+    arithmetic, stored into float32 arrays."""
+    label = np.asarray(label)
+    B, H, W = label.shape
+    C = centers.shape[1]
+    targets = np.zeros((B, H, W, 3 * C), np.float32)
+    weights = np.zeros((B, H, W, 3 * C), np.float32)
+    for b in range(B):
+        for i in range(1, C):                                             # :579
+            y, x = np.where(label[b] == i)                                # :580
+            if len(x) > 0 and centers[b, i, 2] > 0:                       # :583 (class listed in cls_indexes)
+                c = np.zeros((2, 1), np.float32)
+                c[0], c[1] = centers[b, i, 0], centers[b, i, 1]           # :585-586
+                z = centers[b, i, 2]
+                R = np.tile(c, (1, len(x))) - np.vstack((x, y))           # :588  (float64)
+                N = np.linalg.norm(R, axis=0) + 1e-10                     # :590
+                R = np.divide(R, np.tile(N, (2, 1)))                      # :592
+                targets[b, y, x, 3 * i + 0] = R[0, :]                     # :594-596
+                targets[b, y, x, 3 * i + 1] = R[1, :]
+                targets[b, y, x, 3 * i + 2] = np.log(np.float64(z))
+                weights[b, y, x, 3 * i:3 * i + 3] = w_inside              # :600-602
+    return targets, weights
+
+
+def loss_cross_entropy_hard(scores, prob, gt, threshold):
+    """lib/fcn/train.py:455-465 with labels = Hardlabel(prob, gt, threshold) (network.py:340): float64 accumulation."""
+    mask = hard_label(np.asarray(prob, np.float32), np.asarray(gt, np.int32), threshold).astype(np.float64)
+    ce = -(mask * np.asarray(scores, np.float64)).sum(axis=3)
+    return ce.sum() / (mask.sum() + 1e-10), mask
+
+
+def smooth_l1_loss_vertex(pred, targets, weights, sigma=1.0):
+    """lib/fcn/train.py:564-573 in float32 element arithmetic, float64 accumulation.  Returns (loss, d loss / d pred)."""
+    s2 = np.float32(sigma) ** 2
+    diff = np.asarray(weights, np.float32) * (np.asarray(pred, np.float32) - np.asarray(targets, np.float32))
+    ad = np.abs(diff)
+    sign = (ad < np.float32(1.0) / s2).astype(np.float32)
+    in_loss = diff * diff * (s2 / np.float32(2)) * sign + (ad - np.float32(0.5) / s2) * (np.float32(1) - sign)
+    wsum = np.asarray(weights, np.float64).sum() + 1e-10
+    g = np.where(sign > 0, diff * s2, np.sign(diff)) * np.asarray(weights, np.float32)
+    return in_loss.astype(np.float64).sum() / wsum, (g / wsum).astype(np.float32)

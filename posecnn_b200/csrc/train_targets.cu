@@ -1,0 +1,248 @@
+// train_targets.cu — training-side target generation and fused losses.
+//
+//   pcnn_vertex_targets_fwd      lib/gt_synthesize_layer/minibatch.py:543-602 (_generate_vertex_targets, the
+//                                single-instance branch :578-599): per labelled pixel of a present class
+//                                (dx, dy) / (|(dx, dy)| + 1e-10) toward the projected centre and log z; weights = W_INSIDE
+//   pcnn_loss_cls_hard_fwd       lib/fcn/train.py:455-465 (loss_cross_entropy_single_frame) applied to the Hardlabel mask
+//                                (hard_label_op_gpu.cu.cc:16-29) WITHOUT materialising the [B,H,W,C] mask
+//   pcnn_smooth_l1_vertex_fwd    lib/fcn/train.py:564-573 (smooth_l1_loss_vertex)
+// Losses: fixed 592-CTA grid, per-CTA partial sums in double, last CTA to finish reduces them in index order
+// (run-to-run deterministic), optional gradient pass w.r.t. the first input.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pcnn {
+
+constexpr int kLossBlocks = kNumSMs * 4;
+constexpr int kLossThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// vertex targets: thread = one channel pair (float2) of one pixel; consecutive lanes -> consecutive pairs
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_vertex_targets(const int* __restrict__ label, const float* __restrict__ centers /*[B,C,3] cx, cy, z (z <= 0: absent)*/,
+                 int HW, int W, int C, float w_inside, unsigned total_pairs, float* __restrict__ targets, float* __restrict__ weights)
+{
+    const int P2 = 3 * C / 2 + (3 * C & 1);   // pairs per pixel (3C even in practice; odd tail handled below)
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += gridDim.x * blockDim.x) {
+        const unsigned pix = idx / P2;
+        const int pr = idx - pix * P2;
+        const int b = pix / HW, p = pix - b * HW;
+        const int l = __ldg(label + pix);
+        float t[2] = {0.f, 0.f}, w[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int ch = 2 * pr + e;
+            if (ch >= 3 * C) continue;
+            const int cls = ch / 3, comp = ch - 3 * cls;
+            if (cls != l || l <= 0 || l >= C) continue;
+            const float* cen = centers + ((size_t)b * C + cls) * 3;
+            const float z = cen[2];
+            if (!(z > 0.f)) continue;                     // class not in cls_indexes (minibatch.py:583-584)
+            // numpy: float32 centre minus int64 pixel coordinates -> float64 arithmetic, stored as float32 (:589-597)
+            const double dx = (double)cen[0] - (double)(p % W), dy = (double)cen[1] - (double)(p / W);
+            const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+            t[e] = comp == 0 ? (float)(dx / nrm) : (comp == 1 ? (float)(dy / nrm) : (float)log((double)z));
+            w[e] = w_inside;
+        }
+        const size_t o = (size_t)pix * 3 * C + 2 * pr;
+        if (2 * pr + 1 < 3 * C && ((3 * C) & 1) == 0) {
+            *reinterpret_cast<float2*>(targets + o) = make_float2(t[0], t[1]);
+            *reinterpret_cast<float2*>(weights + o) = make_float2(w[0], w[1]);
+        } else {
+            targets[o] = t[0]; weights[o] = w[0];
+            if (2 * pr + 1 < 3 * C) { targets[o + 1] = t[1]; weights[o + 1] = w[1]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic two-value reduction: per-CTA partials, last CTA sums them in index order
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce2(double& a, double& b, double* sh /*[2 * warps]*/)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { sh[2 * w] = a; sh[2 * w + 1] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0, sb = 0;
+        for (int k = 0; k < nw; k++) { sa += sh[2 * k]; sb += sh[2 * k + 1]; }
+        a = sa; b = sb;
+    }
+}
+
+__device__ __forceinline__ bool finish_partials(double a, double b, double* partial /*[2 * grid]*/, unsigned* ticket, double& ta, double& tb)
+{
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return false;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const volatile double* vp = partial;
+        double sa = 0, sb = 0;
+        for (unsigned k = 0; k < gridDim.x; k++) { sa += vp[2 * k]; sb += vp[2 * k + 1]; }
+        ta = sa; tb = sb;
+        *ticket = 0;                                       // ready for the next launch
+    }
+    return threadIdx.x == 0;
+}
+
+// cross entropy over the pixels Hardlabel selects: gt != -1 and (gt > 0 or prob[gt] < threshold)
+__global__ void __launch_bounds__(kLossThreads)
+k_loss_cls_hard(const float* __restrict__ score /*log-softmax*/, const float* __restrict__ prob, const int* __restrict__ gt, unsigned npix,
+                int C, float threshold, double* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out /*[2]: loss, count*/)
+{
+    __shared__ double sh[2 * kLossThreads / 32];
+    double s = 0, n = 0;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int g = __ldg(gt + p);
+        if (g < 0 || g >= C) continue;                     // -1 = ignore (hard_label_op_gpu.cu.cc:24); out-of-range labels ignored
+        if (g > 0 || __ldg(prob + (size_t)p * C + g) < threshold) { s -= (double)__ldg(score + (size_t)p * C + g); n += 1.0; }
+    }
+    block_reduce2(s, n, sh);
+    double ts, tn;
+    if (finish_partials(s, n, partial, ticket, ts, tn)) {
+        out[0] = (float)(ts / (tn + 1e-10));               // train.py:463
+        out[1] = (float)tn;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_loss_cls_hard_grad(const float* __restrict__ prob, const int* __restrict__ gt, unsigned npix, int C, float threshold,
+                     const float* __restrict__ loss_out, float upstream, float* __restrict__ grad /*[npix, C]*/)
+{
+    const float scale = -upstream / (loss_out[1] + 1e-10f);
+    const size_t total = (size_t)npix * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned p = (unsigned)(i / C);
+        const int c = (int)(i - (size_t)p * C);
+        const int g = __ldg(gt + p);
+        const bool sel = g == c && g >= 0 && (g > 0 || __ldg(prob + (size_t)p * C + g) < threshold);
+        grad[i] = sel ? scale : 0.f;
+    }
+}
+
+// smooth L1 on weighted differences (train.py:564-573)
+__device__ __forceinline__ float sl1_term(float pred, float targ, float wgt, float sigma2, float& dterm)
+{
+    const float diff = wgt * (pred - targ);
+    const float ad = fabsf(diff);
+    const bool quad = ad < 1.f / sigma2;
+    dterm = quad ? diff * sigma2 : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+    return quad ? diff * diff * (sigma2 * 0.5f) : ad - 0.5f / sigma2;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+k_smooth_l1_vertex(const float* __restrict__ pred, const float* __restrict__ targ, const float* __restrict__ wgt, size_t n4 /*float4 count*/,
+                   size_t n, float sigma2, double* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out /*[2]: loss, sum w*/)
+{
+    __shared__ double sh[2 * kLossThreads / 32];
+    double s = 0, sw = 0;
+    float d;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 w4 = ld_stream_f4(reinterpret_cast<const float4*>(wgt) + i);
+        sw += (double)w4.x + (double)w4.y + (double)w4.z + (double)w4.w;
+        if (w4.x == 0.f && w4.y == 0.f && w4.z == 0.f && w4.w == 0.f) continue;   // zero weight -> zero term: skip the other loads
+        const float4 p4 = ld_stream_f4(reinterpret_cast<const float4*>(pred) + i);
+        const float4 t4 = ld_stream_f4(reinterpret_cast<const float4*>(targ) + i);
+        s += (double)sl1_term(p4.x, t4.x, w4.x, sigma2, d) + (double)sl1_term(p4.y, t4.y, w4.y, sigma2, d) +
+             (double)sl1_term(p4.z, t4.z, w4.z, sigma2, d) + (double)sl1_term(p4.w, t4.w, w4.w, sigma2, d);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = 4 * n4; i < n; i++) { sw += (double)wgt[i]; s += (double)sl1_term(pred[i], targ[i], wgt[i], sigma2, d); }
+    block_reduce2(s, sw, sh);
+    double ts, tw;
+    if (finish_partials(s, sw, partial, ticket, ts, tw)) {
+        out[0] = (float)(ts / (tw + 1e-10));               // train.py:572
+        out[1] = (float)tw;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_smooth_l1_vertex_grad(const float* __restrict__ pred, const float* __restrict__ targ, const float* __restrict__ wgt, size_t n, float sigma2,
+                        const float* __restrict__ loss_out, float upstream, float* __restrict__ grad)
+{
+    const float scale = upstream / (loss_out[1] + 1e-10f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float w = wgt[i];
+        float d = 0.f;
+        if (w != 0.f) sl1_term(pred[i], targ[i], w, sigma2, d);
+        grad[i] = w * d * scale;                           // d in_loss / d pred = w * g(diff); smoothL1_sign carries no gradient
+    }
+}
+
+}  // namespace pcnn
+
+using namespace pcnn;
+
+extern "C" int pcnn_train_loss_workspace_bytes(size_t* bytes)
+{
+    PCNN_REQUIRE(bytes, "train_loss_workspace_bytes: NULL pointer");
+    *bytes = sizeof(double) * 2 * kLossBlocks + 16;        // per-CTA partials + ticket (must be zero on first use)
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_vertex_targets_fwd(const int32_t* label, const float* centers, int B, int H, int W, int C, float w_inside,
+                                       float* targets, float* weights, void* stream)
+{
+    PCNN_REQUIRE(label && centers && targets && weights, "vertex_targets: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1, "vertex_targets: bad shape");
+    const int P2 = 3 * C / 2 + (3 * C & 1);
+    const unsigned long long total = (unsigned long long)B * H * W * P2;
+    PCNN_REQUIRE(total < 0xffffffffULL, "vertex_targets: too many elements for 32-bit indexing");
+    int blocks = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)kNumSMs * 32);
+    k_vertex_targets<<<blocks, 256, 0, (cudaStream_t)stream>>>(label, centers, H * W, W, C, w_inside, (unsigned)total, targets, weights);
+    return check_launch("vertex_targets");
+}
+
+extern "C" int pcnn_loss_cls_hard_fwd(const float* score, const float* prob, const int32_t* gt, int B, int H, int W, int C, float threshold,
+                                      float* loss_out, float upstream, float* grad_score, void* workspace, size_t workspace_bytes,
+                                      void* stream)
+{
+    PCNN_REQUIRE(score && prob && gt && loss_out && workspace, "loss_cls_hard: NULL tensor pointer");
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "loss_cls_hard: too many pixels");
+    size_t need = 0;
+    pcnn_train_loss_workspace_bytes(&need);
+    PCNN_REQUIRE(workspace_bytes >= need, "loss_cls_hard: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* partial = (double*)workspace;
+    unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
+    const unsigned npix = (unsigned)B * H * W;
+    k_loss_cls_hard<<<kLossBlocks, kLossThreads, 0, (cudaStream_t)stream>>>(score, prob, gt, npix, C, threshold, partial, ticket, loss_out);
+    if (grad_score)
+        k_loss_cls_hard_grad<<<kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(prob, gt, npix, C, threshold, loss_out, upstream, grad_score);
+    return check_launch("loss_cls_hard");
+}
+
+extern "C" int pcnn_smooth_l1_vertex_fwd(const float* pred, const float* targets, const float* weights, size_t n, float sigma,
+                                         float* loss_out, float upstream, float* grad_pred, void* workspace, size_t workspace_bytes,
+                                         void* stream)
+{
+    PCNN_REQUIRE(pred && targets && weights && loss_out && workspace, "smooth_l1_vertex: NULL tensor pointer");
+    PCNN_REQUIRE(sigma > 0.f, "smooth_l1_vertex: sigma must be positive");
+    PCNN_REQUIRE(((uintptr_t)pred | (uintptr_t)targets | (uintptr_t)weights) % 16 == 0, "smooth_l1_vertex: tensors must be 16-byte aligned");
+    size_t need = 0;
+    pcnn_train_loss_workspace_bytes(&need);
+    PCNN_REQUIRE(workspace_bytes >= need, "smooth_l1_vertex: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* partial = (double*)workspace;
+    unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
+    k_smooth_l1_vertex<<<kLossBlocks, kLossThreads, 0, (cudaStream_t)stream>>>(pred, targets, weights, n / 4, n, sigma * sigma, partial, ticket,
+                                                                                loss_out);
+    if (grad_pred)
+        k_smooth_l1_vertex_grad<<<kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(pred, targets, weights, n, sigma * sigma, loss_out, upstream,
+                                                                                  grad_pred);
+    return check_launch("smooth_l1_vertex");
+}

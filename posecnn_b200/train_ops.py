@@ -1,0 +1,69 @@
+"""Training-side target generation and fused losses on the device.
+
+Names follow the reference: `_generate_vertex_targets` (lib/gt_synthesize_layer/minibatch.py:543-602),
+`loss_cross_entropy_single_frame` on the Hardlabel mask (lib/fcn/train.py:455-465, network.py:340) and
+`smooth_l1_loss_vertex` (lib/fcn/train.py:564-573).  All tensors are CUDA torch tensors; no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import check, f32, lib, ptr, require_cuda, stream
+
+_WS = {}
+
+
+def _workspace(device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _WS:
+        n = ctypes.c_size_t(0)
+        check(lib().pcnn_train_loss_workspace_bytes(ctypes.byref(n)))
+        _WS[key] = torch.zeros(int(n.value), dtype=torch.uint8, device=device)   # zero once: the kernels re-arm the ticket
+    return _WS[key]
+
+
+def generate_vertex_targets(im_label, centers, w_inside=1.0):
+    """im_label [B,H,W] int32; centers [B,C,3] f32 = (cx, cy, z) per class, z <= 0 where the class is not in the image
+    (center[ind] / poses[2,3,ind] of minibatch.py:585-587).  Returns (vertex_targets, vertex_weights) [B,H,W,3C] f32."""
+    lab = require_cuda("im_label", im_label, torch.int32, 3)
+    cen = require_cuda("centers", centers, torch.float32, 3)
+    B, H, W = lab.shape
+    C = cen.shape[1]
+    if cen.shape[0] != B or cen.shape[2] != 3:
+        raise ValueError("centers must be [B,C,3]")
+    targets = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=lab.device)
+    weights = torch.empty_like(targets)
+    check(lib().pcnn_vertex_targets_fwd(ptr(lab), ptr(cen), B, H, W, C, f32(w_inside), ptr(targets), ptr(weights), stream()))
+    return targets, weights
+
+
+def loss_cross_entropy_hard(scores, prob, gt_label, threshold, want_grad=False, upstream=1.0):
+    """-sum(hard_label(prob, gt, threshold) * scores) / (sum(mask) + 1e-10) with scores = log-softmax [B,H,W,C];
+    the mask is never materialised.  Returns (loss [1] view, count [1] view[, grad wrt scores])."""
+    sc = require_cuda("scores", scores, torch.float32, 4)
+    pr = require_cuda("prob", prob, torch.float32, 4)
+    gt = require_cuda("gt_label", gt_label, torch.int32, 3)
+    B, H, W, C = sc.shape
+    out = torch.empty((2,), dtype=torch.float32, device=sc.device)
+    grad = torch.empty_like(sc) if want_grad else None
+    ws = _workspace(sc.device)
+    check(lib().pcnn_loss_cls_hard_fwd(ptr(sc), ptr(pr), ptr(gt), B, H, W, C, f32(threshold), ptr(out), f32(upstream), ptr(grad),
+                                       ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    return (out[0:1], out[1:2], grad) if want_grad else (out[0:1], out[1:2])
+
+
+def smooth_l1_loss_vertex(vertex_pred, vertex_targets, vertex_weights, sigma=1.0, want_grad=False, upstream=1.0):
+    """lib/fcn/train.py:564-573.  Returns (loss [1], sum of weights [1][, grad wrt vertex_pred])."""
+    p = require_cuda("vertex_pred", vertex_pred, torch.float32, vertex_pred.dim())
+    t = require_cuda("vertex_targets", vertex_targets, torch.float32, vertex_pred.dim())
+    w = require_cuda("vertex_weights", vertex_weights, torch.float32, vertex_pred.dim())
+    if t.shape != p.shape or w.shape != p.shape:
+        raise ValueError("vertex_pred, vertex_targets and vertex_weights must have the same shape")
+    out = torch.empty((2,), dtype=torch.float32, device=p.device)
+    grad = torch.empty_like(p) if want_grad else None
+    ws = _workspace(p.device)
+    check(lib().pcnn_smooth_l1_vertex_fwd(ptr(p), ptr(t), ptr(w), ctypes.c_size_t(p.numel()), f32(sigma), ptr(out), f32(upstream),
+                                          ptr(grad), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    return (out[0:1], out[1:2], grad) if want_grad else (out[0:1], out[1:2])

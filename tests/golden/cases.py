@@ -72,3 +72,27 @@ def nms_inputs(seed=77, n=96, num_classes=22, batch=1):
     poses_init = rng.standard_normal((n, 7)).astype(np.float32)
     poses_pred = np.tanh(rng.standard_normal((n, 4 * num_classes))).astype(np.float32)
     return rois, poses_init, poses_pred
+
+
+def vertex_target_inputs(seed=41, H=60, W=80, C=6, B=2):
+    """label maps with a few elliptical objects, per-class projected centres and depths; one class present in the label
+    map but missing from cls_indexes (no targets), one listed class without pixels."""
+    rng = np.random.default_rng(seed)
+    label = np.zeros((B, H, W), np.int32)
+    centers = np.zeros((B, C, 3), np.float32)            # (cx, cy, z); z = 0 -> class not in cls_indexes
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        classes = rng.permutation(np.arange(1, C))[:3]
+        for c in classes:
+            cx, cy = rng.uniform(0.2 * W, 0.8 * W), rng.uniform(0.2 * H, 0.8 * H)
+            a, bb = rng.uniform(6, 14), rng.uniform(6, 14)
+            label[b][((xx - cx) / a) ** 2 + ((yy - cy) / bb) ** 2 <= 1] = c
+            centers[b, c] = (cx + rng.normal(0, 2), cy + rng.normal(0, 2), rng.uniform(0.5, 1.5))
+        centers[b, classes[0], 2] = 0.0                  # labelled but not listed
+        spare = [c for c in range(1, C) if c not in classes]
+        if spare:
+            centers[b, spare[0]] = (10.0, 10.0, 0.9)     # listed but without pixels
+        if b == 0:
+            centers[0, classes[1], 0:2] = (17.0, 23.0)   # integer centre on a pixel: zero vector / (0 + 1e-10)
+            label[0, 23, 17] = classes[1]
+    return label, centers
