@@ -218,3 +218,27 @@ def test_cpu_hough_ransac_config0():
     assert bt.shape[0] % 9 == 0 and bt.shape[0] >= 9   # train mode keeps all surviving hypotheses (refSteps < 4 rule)
     ww, hh = bt[0, 4] - bt[0, 2], bt[0, 5] - bt[0, 3]
     np.testing.assert_allclose(bt[1:9, 4] - bt[1:9, 2], ww, rtol=1e-5); np.testing.assert_allclose(bt[1:9, 5] - bt[1:9, 3], hh, rtol=1e-5)
+
+
+def test_result_records_roundtrip(tmp_path):
+    """Record layout handed to ICP / the .mat writer (lib/fcn/test.py:1327-1351,1415-1423, lov.py:431-438)."""
+    import scipy.io
+    from posecnn_b200.utils import results
+    rec = np.zeros((8, 15), np.float32)
+    rec[0] = [1, 5, 10, 20, 110, 220, 900, 1, 0, 0, 0, 0.1, 0.2, 0.9, 1]
+    rec[1] = [0, 3, 30, 40, 90, 100, 700, 0.5, 0.5, 0.5, 0.5, -0.1, 0.0, 1.1, 1]
+    rec[2] = [1, 7, 50, 60, 70, 80, 500, 0, 1, 0, 0, 0.0, 0.3, 0.7, 1]
+    per_image = results.split_detections(rec, batch=2)
+    assert [r.shape[0] for r, _ in per_image] == [1, 2]
+    rois, poses = per_image[1]
+    assert rois[:, 1].tolist() == [5.0, 7.0] and poses[1].tolist() == rec[2, 7:14].tolist()
+    seg = results.segmentation_record(np.zeros((480, 640), np.int32), rois, poses)
+    assert sorted(seg) == ["labels", "poses", "poses_icp", "poses_refined", "rois"] and seg["poses_icp"].shape == (2, 7)
+    p = results.icp_parameters([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]], 10000.0)
+    np.testing.assert_allclose(p, [1066.778, 1067.487, 312.9869, 241.3109, 0.25, 6.0, 10000.0], rtol=1e-6)
+    f = str(tmp_path / "000001.mat")
+    results.save_mat(f, seg)
+    back = scipy.io.loadmat(f)
+    np.testing.assert_array_equal(back["rois"], rois)
+    np.testing.assert_array_equal(back["poses"], poses)
+    assert back["labels"].shape == (480, 640)
