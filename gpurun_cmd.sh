@@ -1,23 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_train_ops_gpu.py -m gpu -x -q 2>&1 | tail -15
-timeout 300 python - <<'PY'
-import torch, numpy as np, time
-from posecnn_b200 import train_ops, synth
-dev=torch.device('cuda:0')
-B,H,W,C=32,480,640,22
-sc=synth.make_scene(batch=4,height=H,width=W,num_classes=C,seed=5)
-label=torch.from_numpy(np.tile(sc['label'],(8,1,1))).to(dev)
-cen=torch.rand((B,C,3),device=dev)*400+1
-def ev(fn,n=10):
-    fn(); torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True); e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)/n
-t=ev(lambda: train_ops.generate_vertex_targets(label,cen,10.0)); print(f"vertex_targets B=32: {t:.3f} ms  ({2*B*H*W*3*C*4/t/1e6:.0f} GB/s written)")
-tg,wg=train_ops.generate_vertex_targets(label,cen,10.0); pred=torch.randn_like(tg)
-t=ev(lambda: train_ops.smooth_l1_loss_vertex(pred,tg,wg,1.0)); print(f"smooth_l1 fwd B=32: {t:.3f} ms ({B*H*W*3*C*4*(1+2*0.05)/t/1e6:.0f} GB/s min-traffic)")
-t=ev(lambda: train_ops.smooth_l1_loss_vertex(pred,tg,wg,1.0,want_grad=True)); print(f"smooth_l1 fwd+grad B=32: {t:.3f} ms")
-score=torch.log_softmax(torch.randn((B,H,W,C),device=dev),3); prob=score.exp(); gt=label.clone()
-t=ev(lambda: train_ops.loss_cross_entropy_hard(score,prob,gt,1.0)); print(f"cls loss fused B=32: {t:.3f} ms")
-from posecnn_b200.hard_label_layer import hard_label_op
-t=ev(lambda: -(hard_label_op.hard_label(prob,gt,1.0)*score).sum()); print(f"cls loss un-fused (Hardlabel op + torch mul/sum) B=32: {t:.3f} ms")
-PY
+timeout 900 python -m pytest tests/test_train_ops_gpu.py tests/test_network_gpu.py -m gpu -x -q 2>&1 | tail -15

@@ -195,7 +195,7 @@ class vgg16_convs:
             i += 1
         return feats
 
-    def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True):
+    def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True, want_score=False):
         """Inference / forward pass.  data [B,H,W,3] (u8 BGR or pre-processed f32), H, W multiples of 16
         (pad_im, lib/utils/blob.py:48-58).  Returns self.layers with the reference's layer names."""
         C = self.num_classes
@@ -232,11 +232,14 @@ class vgg16_convs:
         label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
         vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
         prob = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_prob else None
+        score = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_score else None
         check(lib().pcnn_up8_heads(ptr(lowres), ptr(P["score/biases"]), ptr(P["vertex_pred/biases"]), B, h, w, C, ptr(label),
-                                   ptr(vertex), ptr(prob), ptr(None), stream()))
+                                   ptr(vertex), ptr(prob), ptr(score), stream()))
         L["label_2d"], L["vertex_pred"] = label, vertex
         if want_prob:
             L["prob_normalized"] = prob
+        if want_score:
+            L["score"] = score
         if not self.vertex_reg_2d:
             return L
         box, pose, target, weight, domain, num_rois, status = hough_voting_gpu_op.hough_voting_gpu_capacity(
@@ -267,6 +270,32 @@ class vgg16_convs:
             if self.pose_reg:
                 L["poses_tanh"] = L["poses_tanh"][:n]
         return L
+
+
+def training_losses(net: vgg16_convs, layers: dict, gt_label_2d, vertex_targets, vertex_weights, points, symmetry,
+                    vertex_w: float = 1.0, margin: float = 0.01) -> dict:
+    """The loss heads of the reference's training graph on the outputs of `forward(..., want_prob=True, want_score=True)`
+    of an `is_train` network (lib/fcn/train.py:486-500, vgg16_convs.py:141-147,195-200):
+      loss_cls    = cross entropy of log_softmax(score) over the Hardlabel selection (fused, mask not materialised)
+      loss_vertex = VERTEX_W * smooth_l1_loss_vertex(vertex_pred, vertex_targets, vertex_weights)
+      loss_pose   = Averagedistance(l2_normalize(poses_tanh * poses_weight), poses_target, poses_weight, points, symmetry)
+    Returns the three losses and their sum as [1] tensors (no host synchronisation)."""
+    from .. import train_ops
+    from ..average_distance_loss import average_distance_loss_op
+    logp = torch.log_softmax(layers["score"], dim=3)                                    # network.py:491-506
+    loss_cls, _ = train_ops.loss_cross_entropy_hard(logp, layers["prob_normalized"], gt_label_2d, net.threshold_label)
+    loss_vertex, _ = train_ops.smooth_l1_loss_vertex(layers["vertex_pred"], vertex_targets, vertex_weights)
+    out = dict(loss_cls=loss_cls, loss_vertex=vertex_w * loss_vertex)
+    total = out["loss_cls"] + out["loss_vertex"]
+    if net.pose_reg:
+        mul = layers["poses_tanh"] * layers["poses_weight"]                             # vgg16_convs.py:195-196
+        pred = mul / mul.pow(2).sum(1, keepdim=True).clamp(min=1e-12).sqrt()            # tf.nn.l2_normalize(dim=1)
+        loss_pose, pose_diff = average_distance_loss_op.average_distance_loss(pred.contiguous(), layers["poses_target"].contiguous(),
+                                                                              layers["poses_weight"].contiguous(), points, symmetry, margin)
+        out.update(loss_pose=loss_pose, poses_pred=pred, poses_pred_diff=pose_diff)
+        total = total + loss_pose
+    out["loss"] = total
+    return out
 
 
 class GraphedForward:

@@ -96,3 +96,53 @@ def test_smooth_l1_loss_vertex(cuda, sigma, n):
     l = ((d ** 2) * (s2 / 2) * sign + (d.abs() - 0.5 / s2) * (1 - sign)).sum() / (T(wgt, cuda).double().sum() + 1e-10)
     l.backward()
     assert torch.allclose(grad.double(), p.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_training_loss_heads_compose(cuda):
+    """configs[4] shape in miniature (a GPU's share of the batch): is_train network forward -> Hough in train mode
+    (9 jittered rows per ROI, quaternion targets from the gt poses) -> RoiPool -> pose head -> the three training losses,
+    each against the oracle composition on the network's own intermediate tensors."""
+    from posecnn_b200 import synth, train_ops
+    from posecnn_b200.networks.vgg16_convs import training_losses, vgg16_convs
+    C, B, H, W = 6, 2, 64, 96
+    net = vgg16_convs(num_classes=C, device=cuda, is_train=True).init_random(seed=0, bias_std=0.05)
+    rgb, _ = synth.make_images(B, H, W, seed=3)
+    data = torch.from_numpy(rgb).to(cuda)
+    meta = torch.from_numpy(np.stack([synth.make_meta(synth.intrinsics(H, W))] * B)).to(cuda)
+    ext = torch.from_numpy(synth.extents_for(C)).to(cuda)
+    rng = np.random.default_rng(8)
+    gt = np.zeros((2 * (C - 1), 13), np.float32)                      # gt pose rows [batch, cls, (5 unused), qw..qz, t]
+    for i in range(gt.shape[0]):
+        q = rng.standard_normal(4); q /= np.linalg.norm(q)
+        gt[i, 0], gt[i, 1] = i % B, 1 + i // B
+        gt[i, 2:6] = (10, 10, 80, 60); gt[i, 6:10] = q; gt[i, 10:13] = (0.0, 0.0, 1.0)
+    out = net.forward(data, meta, ext, poses=torch.from_numpy(gt).to(cuda), want_prob=True, want_score=True)
+    label = to_np(out["label_2d"])
+    u = rng.random(label.shape)                                                         # 10 % ignore, 30 % disagreeing labels
+    gt_label = np.where(u < 0.1, -1, np.where(u < 0.4, rng.integers(0, C, label.shape), label)).astype(np.int32)
+    centers = np.zeros((B, C, 3), np.float32)
+    for b in range(B):
+        for c in np.unique(label[b]):
+            if c > 0:
+                ys, xs = np.where(label[b] == c)
+                centers[b, c] = (xs.mean(), ys.mean(), 0.8 + 0.1 * c)
+    vt, vw = train_ops.generate_vertex_targets(T(label, cuda), T(centers, cuda), 10.0)
+    points = T(synth.make_model_points(C, 200, seed=2), cuda)
+    symmetry = torch.zeros((C,), device=cuda); symmetry[2] = 1.0
+    losses = training_losses(net, out, T(gt_label, cuda), vt, vw, points, symmetry, vertex_w=1.0)
+    # classification: log-softmax of the kernel's own scores, Hardlabel selection
+    score = to_np(out["score"]).astype(np.float64)
+    logp = score - np.log(np.exp(score - score.max(3, keepdims=True)).sum(3, keepdims=True)) - score.max(3, keepdims=True)
+    want_cls, _ = oracle.loss_cross_entropy_hard(logp, to_np(out["prob_normalized"]), gt_label, 1.0)
+    assert want_cls > 1e-3 and abs(float(losses["loss_cls"].item()) - want_cls) <= 2e-5 * abs(want_cls)
+    want_v, _ = oracle.smooth_l1_loss_vertex(to_np(out["vertex_pred"]), to_np(vt), to_np(vw), 1.0)
+    assert abs(float(losses["loss_vertex"].item()) - want_v) <= 1e-5 * abs(want_v)
+    # pose: rows come in groups of 9 per ROI in train mode; weights select the gt class quaternion
+    assert out["rois"].shape[0] % 9 == 0 and out["poses_weight"].shape == out["poses_tanh"].shape
+    pt, pw, ptg = to_np(out["poses_tanh"]), to_np(out["poses_weight"]), to_np(out["poses_target"])
+    mul = pt * pw
+    pred = mul / np.sqrt(np.maximum((mul ** 2).sum(1, keepdims=True), 1e-12))
+    want_p, _ = oracle.average_distance_loss(pred.astype(np.float32), ptg, pw, to_np(points), to_np(symmetry), 0.01)
+    assert abs(float(losses["loss_pose"].item()) - float(want_p[0])) <= 1e-4 * max(abs(float(want_p[0])), 1e-6)
+    total = float(losses["loss_cls"].item()) + float(losses["loss_vertex"].item()) + float(losses["loss_pose"].item())
+    assert abs(float(losses["loss"].item()) - total) <= 1e-5 * abs(total)
