@@ -432,10 +432,7 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
     __shared__ int4 s_q[kWarps][64];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int total = work_ctr[1];
-    // a warp covers 32 / R samples x R rows per iteration (R is a power of two <= 32)
-    const int rl = lane & (R - 1);   // row of the band owned by this lane
-    const int sub = lane / R;        // which of the warp's samples
-    const int spw = 32 / R;
+    // R (rows per band) is a power of two <= 32
     while (true) {
         __syncthreads();
         if (t == 0) s_item = atomicAdd(&work_ctr[0], 1);
@@ -456,8 +453,6 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
 
         const int ns = cls_nsamp[b * C + c];
         const Sample* S = samples + (size_t)b * samp_cap + cls_soff[b * C + c];
-        const int cy = r0 + rl;
-        int* Drow = D + rl * stride - xlo;
         int4* Q = s_q[w];   // this warp's queue of (sample, row) pairs whose end points need the exact check
         int qn = 0;         // warp-uniform
         const unsigned lt = (1u << lane) - 1u;
@@ -504,17 +499,21 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
             __syncwarp();
         };
 
-        // software pipeline: the record of the next iteration is in flight while this one is processed
-        int sidx = w * spw + sub;
+        // lane = sample: 32 samples per warp iteration, each lane walks the R rows of the band with a per-lane
+        // rotation of the start row, so that at any moment the lanes touch different rows of the difference array.
+        // The record decode, the reach test and the bounds are done once per (sample, band) instead of once per
+        // (sample, row); warps whose 32 samples (consecutive in raster order) do not reach the band leave at once.
+        // The record of the next iteration is in flight while this one is processed.
+        int sidx = w * 32 + lane;
         float4 n0 = make_float4(0, 0, 0, 0), n1v = n0;
         if (sidx < ns) {
             n0 = __ldg(reinterpret_cast<const float4*>(S + sidx));
             n1v = __ldg(reinterpret_cast<const float4*>(S + sidx) + 1);
         }
-        for (int sb = w * spw; sb < ns; sb += kWarps * spw) {
+        for (int sb = w * 32; sb < ns; sb += kWarps * 32) {
             const float4 q0 = n0, q1 = n1v;
             const int scur = sidx;
-            sidx += kWarps * spw;
+            sidx += kWarps * 32;
             if (sidx < ns) {
                 n0 = __ldg(reinterpret_cast<const float4*>(S + sidx));
                 n1v = __ldg(reinterpret_cast<const float4*>(S + sidx) + 1);
@@ -524,66 +523,76 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
             const int mflags = __float_as_int(q1.z);
             const int m = (int)(short)(mflags & 0xffff);
             const int fl = mflags >> 16;
-            const int idy = cy - y;
-            int act = 0;      // 0 nothing, 1 interval [a, e] trusted, 2 queued for the exact check
-            int a = 0, e = 0, mode = 0;
-            if (scur < ns && rl < nrows && m >= 0 && abs(idy) <= m) {
-                const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
-                if (idy == 0) {
-                    // the pixel's own row: cos = sign(dx) * u / n1, decided once per sample in k_emit
-                    if (fl & 64) { a = x + 1; e = wmax; act = a <= e; }
-                    else if (fl & 128) { a = wmin; e = x - 1; act = a <= e; }
-                } else {
-                    const bool v1 = idy > 0 ? (fl & 1) : (fl & 2);
-                    const bool v2 = idy > 0 ? (fl & 4) : (fl & 8);
-                    if (v1 || v2) {
-                        const float dy = (float)idy;
-                        const float h1 = dy * q1.x, h2 = dy * q1.y;
-                        float lo, hi;
-                        if (v1 && v2) { lo = fminf(h1, h2); hi = fmaxf(h1, h2); }
-                        else {
-                            const float hh = v1 ? h1 : h2;
-                            const bool up = v1 ? (fl & 16) : (fl & 32);
-                            lo = up ? hh : -1e9f;
-                            hi = up ? 1e9f : hh;
-                        }
-                        lo = fminf(fmaxf(lo, -40000.f), 40000.f);
-                        hi = fminf(fmaxf(hi, -40000.f), 40000.f);
-                        a = x + (int)ceilf(lo);
-                        e = x + (int)floorf(hi);
-                        // The ray estimate and the fp32 predicate both sit within ~1e-6 (dy^2 + m^2) / |dy| cells
-                        // of the real cone boundary; an end point closer than tau to an integer
-                        // is re-checked with the reference predicate, the others are exact as they are.
-                        const float tau = 0.03f + 2e-6f * __fdividef(dy * dy + (float)(m * m), fabsf(dy));
-                        if (a > e) {
-                            const bool ca = (float)(a - x) - hi < tau && a >= wmin && a <= wmax;
-                            const bool ce = lo - (float)(e - x) < tau && e >= wmin && e <= wmax;
-                            if (ca || ce) { act = 2; mode = (ca ? 4 : 0) | (ce ? 8 : 0); }
-                        } else {
-                            const float ma = (float)(a - x) - lo, me = hi - (float)(e - x);
-                            const bool va = a >= wmin && (ma < tau || ma > 1.f - tau);
-                            const bool ve = e <= wmax && (me < tau || me > 1.f - tau);
-                            a = max(a, wmin);
-                            e = min(e, wmax);
-                            if (a <= e) { act = (va || ve) ? 2 : 1; mode = (va ? 1 : 0) | (ve ? 2 : 0); }
+            // rows of the band this sample reaches: |cy - y| <= m
+            const int row_lo = max(y - m, r0) - r0, row_hi = min(y + m, r0 + nrows - 1) - r0;
+            const bool reach = scur < ns && m >= 0 && row_lo <= row_hi;
+            if (!__any_sync(0xffffffffu, reach)) continue;
+            const int wmin = max(x - m, 0), wmax = min(x + m, W - 1);
+            const float fm2 = (float)(m * m);
+#pragma unroll 1
+            for (int k = 0; k < R; k++) {
+                const int rl = (lane + k) & (R - 1);
+                const int idy = r0 + rl - y;
+                int act = 0;      // 0 nothing, 1 interval [a, e] trusted, 2 queued for the exact check
+                int a = 0, e = 0, mode = 0;
+                if (reach && rl >= row_lo && rl <= row_hi) {
+                    if (idy == 0) {
+                        // the pixel's own row: cos = sign(dx) * u / n1, decided once per sample in k_emit
+                        if (fl & 64) { a = x + 1; e = wmax; act = a <= e; }
+                        else if (fl & 128) { a = wmin; e = x - 1; act = a <= e; }
+                    } else {
+                        const bool v1 = idy > 0 ? (fl & 1) : (fl & 2);
+                        const bool v2 = idy > 0 ? (fl & 4) : (fl & 8);
+                        if (v1 || v2) {
+                            const float dy = (float)idy;
+                            const float h1 = dy * q1.x, h2 = dy * q1.y;
+                            float lo, hi;
+                            if (v1 && v2) { lo = fminf(h1, h2); hi = fmaxf(h1, h2); }
+                            else {
+                                const float hh = v1 ? h1 : h2;
+                                const bool up = v1 ? (fl & 16) : (fl & 32);
+                                lo = up ? hh : -1e9f;
+                                hi = up ? 1e9f : hh;
+                            }
+                            lo = fminf(fmaxf(lo, -40000.f), 40000.f);
+                            hi = fminf(fmaxf(hi, -40000.f), 40000.f);
+                            a = x + (int)ceilf(lo);
+                            e = x + (int)floorf(hi);
+                            // The ray estimate and the fp32 predicate both sit within ~1e-6 (dy^2 + m^2) / |dy| cells
+                            // of the real cone boundary; an end point closer than tau to an integer
+                            // is re-checked with the reference predicate, the others are exact as they are.
+                            const float tau = 0.03f + 2e-6f * __fdividef(dy * dy + fm2, fabsf(dy));
+                            if (a > e) {
+                                const bool ca = (float)(a - x) - hi < tau && a >= wmin && a <= wmax;
+                                const bool ce = lo - (float)(e - x) < tau && e >= wmin && e <= wmax;
+                                if (ca || ce) { act = 2; mode = (ca ? 4 : 0) | (ce ? 8 : 0); }
+                            } else {
+                                const float ma = (float)(a - x) - lo, me = hi - (float)(e - x);
+                                const bool va = a >= wmin && (ma < tau || ma > 1.f - tau);
+                                const bool ve = e <= wmax && (me < tau || me > 1.f - tau);
+                                a = max(a, wmin);
+                                e = min(e, wmax);
+                                if (a <= e) { act = (va || ve) ? 2 : 1; mode = (va ? 1 : 0) | (ve ? 2 : 0); }
+                            }
                         }
                     }
                 }
-            }
-            if (act == 1) {
-                atomicAdd(&Drow[a], 1);
-                atomicAdd(&Drow[e + 1], -1);
-            }
-            const unsigned need = __ballot_sync(0xffffffffu, act == 2);
-            if (need) {
-                if (act == 2) Q[qn + __popc(need & lt)] = make_int4(scur, rl | (mode << 8), a, e);
-                qn += __popc(need);
-                __syncwarp();
-                if (qn >= 32) {
-                    drain(32);
-                    if (lane < qn - 32) Q[lane] = Q[32 + lane];
-                    qn -= 32;
+                if (act == 1) {
+                    int* Drow = D + rl * stride - xlo;
+                    atomicAdd(&Drow[a], 1);
+                    atomicAdd(&Drow[e + 1], -1);
+                }
+                const unsigned need = __ballot_sync(0xffffffffu, act == 2);
+                if (need) {
+                    if (act == 2) Q[qn + __popc(need & lt)] = make_int4(scur, rl | (mode << 8), a, e);
+                    qn += __popc(need);
                     __syncwarp();
+                    if (qn >= 32) {
+                        drain(32);
+                        if (lane < qn - 32) Q[lane] = Q[32 + lane];
+                        qn -= 32;
+                        __syncwarp();
+                    }
                 }
             }
         }
