@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_hough_gpu.py tests/test_reference_kernels_gpu.py -m gpu -x -q 2>&1 | tail -5
-timeout 600 python bench.py --workload hough --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_hough.json 2> gpurun_out/bench_hough.err; python - <<'PY'
-import json; d=json.loads(open('gpurun_out/bench_hough.json').read().strip().splitlines()[-1]); print('hough', d['value'], d['ms_per_step'], d['roofline']['frac'])
-PY
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; python - <<'PY'
-import json; d=json.loads(open('gpurun_out/bench_full.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['breakdown_ms'], d['e2e']['value'])
-PY
+for s in 20 100; do timeout 300 python bench.py --workload hough --batch 1 --steps $s --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('steps', d['steps'], 'ms', d['ms_per_step'])"; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 python bench.py --workload hough --batch 1 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | grep -E "^  [a-zA-Z].*\(|gpu__time" | paste - - | awk '{print $NF, $1, $2}' | tail -18

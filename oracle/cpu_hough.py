@@ -65,7 +65,7 @@ def _host_cores():
 def _best_threads(probe_args, limit=None):
     """The op's OpenMP regions are short (per class, per RANSAC round): more threads are not always faster and on a
     128-thread host the all-cores run is ~60x SLOWER than one thread.  "All the host threads it can use" is therefore
-    decided by measurement: time a 2-frame probe at 1, 2, 4, ... , all cores and keep the fastest."""
+    decided by measurement: time a probe batch at 1, 2, 4, ... , all cores and keep the fastest."""
     n = limit or _host_cores()
     cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, n) if c <= n})
     timing = {}
@@ -87,13 +87,13 @@ def timed_baseline(sample_frames=32, threads=None, repeats=5):
     """frames/s of the CPU op on `sample_frames` synthetic 640x480 / 22-class frames (same generator and shapes as the
     GPU workload); best-effort variant: -O3, OpenMP on, thread count = the fastest of a measured sweep (see
     _best_threads); the as-shipped single-thread figure is reported beside it."""
-    probe = _bench_frames(2)
-    pa = (probe["label"], probe["vertex"], probe["extents"], probe["meta"])
+    sc = _bench_frames(sample_frames)
+    args = (sc["label"], sc["vertex"], sc["extents"], sc["meta"])
+    npb = min(8, sample_frames)
+    pa = (sc["label"][:npb], sc["vertex"][:npb], sc["extents"], sc["meta"][:npb])      # 8-frame probe for the sweep
     sweep = None
     if threads is None:
         threads, sweep = _best_threads(pa)
-    sc = _bench_frames(sample_frames)
-    args = (sc["label"], sc["vertex"], sc["extents"], sc["meta"])
     hough_voting(*args, threads=threads)  # warm-up
     ts = []
     for _ in range(repeats):
@@ -102,11 +102,11 @@ def timed_baseline(sample_frames=32, threads=None, repeats=5):
         ts.append(time.perf_counter() - t0)
     t0 = time.perf_counter()
     hough_voting(*pa, threads=1)
-    t1 = (time.perf_counter() - t0) / 2
+    t1 = (time.perf_counter() - t0) / npb
     dt = float(np.median(ts))
     return dict(value=sample_frames / dt, unit="frames/s", cores=threads, kind="port",
                 sample=f"{sample_frames} synthetic 640x480x22-class frames x {repeats} runs, CPU hough_voting_layer (RANSAC) "
-                       f"restated in C++ (-O3 -fopenmp); {threads} threads = fastest of the sweep {sweep} (ms per 2-frame probe) "
+                       f"restated in C++ (-O3 -fopenmp); {threads} threads = fastest of the sweep {sweep} (ms per {npb}-frame probe) "
                        f"on {_host_cores()} host cores; as-shipped 1-thread: {1.0 / t1:.2f} frames/s",
                 ms_per_frame=1e3 * dt / sample_frames, single_thread_frames_per_s=1.0 / t1, host_cores=_host_cores(),
                 thread_sweep_ms=sweep)
@@ -116,10 +116,9 @@ def reference_arm(args):
     """`bench.py --impl reference`: the reference's own CPU implementation of the path on host cores (thread count =
     the fastest of a measured sweep; all cores is far from the fastest for this op)."""
     frames = 32
-    probe = _bench_frames(2)
-    cores, sweep = _best_threads((probe["label"], probe["vertex"], probe["extents"], probe["meta"]))
     sc = _bench_frames(frames)
     a = (sc["label"], sc["vertex"], sc["extents"], sc["meta"])
+    cores, sweep = _best_threads((sc["label"][:8], sc["vertex"][:8], sc["extents"], sc["meta"][:8]))
     for _ in range(max(1, min(args.warmup, 2))):
         hough_voting(*a, threads=cores)
     t0 = time.perf_counter()
@@ -133,5 +132,5 @@ def reference_arm(args):
                 config=dict(workload=f"CPU hough_voting_layer (RANSAC), {frames} frames 640x480x22 per step"),
                 cpu_baseline=dict(value=v, unit="frames/s", cores=cores, kind="port", host_cores=_host_cores(),
                                   sample=f"{frames} frames per step, {args.steps} steps, {cores} OpenMP threads (fastest of sweep "
-                                         f"{sweep} ms per 2-frame probe)"),
+                                         f"{sweep} ms per 8-frame probe)"),
                 e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
