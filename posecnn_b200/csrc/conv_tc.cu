@@ -369,7 +369,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 
 // ---------------------------------------------------------------------------------------------
 // Row mode for the K-small layers (conv1_2, conv2_x: Cin, Cout <= 128), which are bound by L2 -> SM operand
-// traffic in the tile kernel (every tap re-fetches its A tile; profiles/r01_conv_tc_ncu_full.txt).
+// traffic in the tile kernel (every tap re-fetches its A tile; profiles/r01_conv_tile_kernel_ncu_full_early.txt).
 // A work item is TWO output rows x 128 pixels of one image:
 //   * per 64-channel chunk ONE TMA box {64 ch, 130 px, 4 rows} (halo included) is loaded; the A operand of
 //     tap (r, s) for output row j is the 128 consecutive patch rows starting at ((r + j) * 130 + s): a
