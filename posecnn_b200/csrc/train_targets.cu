@@ -185,9 +185,97 @@ k_smooth_l1_vertex_grad(const float* __restrict__ pred, const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused vertex loss: smooth_l1_loss_vertex(vertex_pred, targets(label, centers), weights(label, centers)) without
+// the two [B,H,W,3C] target / weight tensors (5.2 GB at batch 32): only the three channels of a labelled pixel's own
+// class carry weight, so the kernel reads 12 bytes of vertex_pred per foreground pixel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pixel_targets(const int* __restrict__ label, const float* __restrict__ centers, unsigned pix, int HW,
+                                              int W, int C, int& cls, float t[3])
+{
+    const int l = __ldg(label + pix);
+    if (l <= 0 || l >= C) return false;
+    const int b = pix / HW, p = pix - b * HW;
+    const float* cen = centers + ((size_t)b * C + l) * 3;
+    const float z = cen[2];
+    if (!(z > 0.f)) return false;
+    const double dx = (double)cen[0] - (double)(p % W), dy = (double)cen[1] - (double)(p / W);
+    const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+    t[0] = (float)(dx / nrm); t[1] = (float)(dy / nrm); t[2] = (float)log((double)z);
+    cls = l;
+    return true;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+k_vertex_loss_fused(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW,
+                    int W, int C, float w_inside, float sigma2, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                    float* __restrict__ out)
+{
+    __shared__ double sh[2 * kLossThreads / 32];
+    double s = 0, sw = 0;
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        int cls;
+        float t[3], d;
+        if (!pixel_targets(label, centers, pix, HW, W, C, cls, t)) continue;
+        const float* pp = pred + (size_t)pix * 3 * C + 3 * cls;
+#pragma unroll
+        for (int k = 0; k < 3; k++) s += (double)sl1_term(__ldg(pp + k), t[k], w_inside, sigma2, d);
+        sw += 3.0 * (double)w_inside;
+    }
+    block_reduce2(s, sw, sh);
+    double ts, tw;
+    if (finish_partials(s, sw, partial, ticket, ts, tw)) {
+        out[0] = (float)(ts / (tw + 1e-10));
+        out[1] = (float)tw;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_vertex_loss_fused_grad(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ centers, unsigned npix,
+                         int HW, int W, int C, float w_inside, float sigma2, const float* __restrict__ loss_out, float upstream,
+                         float* __restrict__ grad /*zero-filled*/)
+{
+    const float scale = upstream / (loss_out[1] + 1e-10f);
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        int cls;
+        float t[3], d;
+        if (!pixel_targets(label, centers, pix, HW, W, C, cls, t)) continue;
+        const size_t o = (size_t)pix * 3 * C + 3 * cls;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            sl1_term(__ldg(pred + o + k), t[k], w_inside, sigma2, d);
+            grad[o + k] = w_inside * d * scale;
+        }
+    }
+}
+
 }  // namespace pcnn
 
 using namespace pcnn;
+
+extern "C" int pcnn_vertex_loss_fused_fwd(const float* pred, const int32_t* label, const float* centers, int B, int H, int W, int C,
+                                          float w_inside, float sigma, float* loss_out, float upstream, float* grad_pred,
+                                          void* workspace, size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(pred && label && centers && loss_out && workspace, "vertex_loss_fused: NULL tensor pointer");
+    PCNN_REQUIRE(sigma > 0.f && B >= 1 && H >= 1 && W >= 1 && C >= 1, "vertex_loss_fused: bad arguments");
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "vertex_loss_fused: too many pixels");
+    size_t need = 0;
+    pcnn_train_loss_workspace_bytes(&need);
+    PCNN_REQUIRE(workspace_bytes >= need, "vertex_loss_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* partial = (double*)workspace;
+    unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
+    const unsigned npix = (unsigned)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_vertex_loss_fused<<<kLossBlocks, kLossThreads, 0, st>>>(pred, label, centers, npix, H * W, W, C, w_inside, sigma * sigma, partial, ticket,
+                                                               loss_out);
+    if (grad_pred) {
+        cudaMemsetAsync(grad_pred, 0, sizeof(float) * (size_t)npix * 3 * C, st);
+        k_vertex_loss_fused_grad<<<kNumSMs * 16, 256, 0, st>>>(pred, label, centers, npix, H * W, W, C, w_inside, sigma * sigma, loss_out,
+                                                                upstream, grad_pred);
+    }
+    return check_launch("vertex_loss_fused");
+}
 
 extern "C" int pcnn_train_loss_workspace_bytes(size_t* bytes)
 {

@@ -273,18 +273,22 @@ class vgg16_convs:
 
 
 def training_losses(net: vgg16_convs, layers: dict, gt_label_2d, vertex_targets, vertex_weights, points, symmetry,
-                    vertex_w: float = 1.0, margin: float = 0.01) -> dict:
+                    vertex_w: float = 1.0, margin: float = 0.01, centers=None, vertex_w_inside: float = 10.0) -> dict:
     """The loss heads of the reference's training graph on the outputs of `forward(..., want_prob=True, want_score=True)`
     of an `is_train` network (lib/fcn/train.py:486-500, vgg16_convs.py:141-147,195-200):
       loss_cls    = cross entropy of log_softmax(score) over the Hardlabel selection (fused, mask not materialised)
       loss_vertex = VERTEX_W * smooth_l1_loss_vertex(vertex_pred, vertex_targets, vertex_weights)
+                    (vertex_targets=None + centers [B,C,3]: the fused kernel that derives targets from gt_label_2d / centers)
       loss_pose   = Averagedistance(l2_normalize(poses_tanh * poses_weight), poses_target, poses_weight, points, symmetry)
     Returns the three losses and their sum as [1] tensors (no host synchronisation)."""
     from .. import train_ops
     from ..average_distance_loss import average_distance_loss_op
     logp = torch.log_softmax(layers["score"], dim=3)                                    # network.py:491-506
     loss_cls, _ = train_ops.loss_cross_entropy_hard(logp, layers["prob_normalized"], gt_label_2d, net.threshold_label)
-    loss_vertex, _ = train_ops.smooth_l1_loss_vertex(layers["vertex_pred"], vertex_targets, vertex_weights)
+    if vertex_targets is None:   # fused path: targets / weights are functions of (labels, projected centres), never materialised
+        loss_vertex, _ = train_ops.vertex_loss_from_centers(layers["vertex_pred"], gt_label_2d, centers, vertex_w_inside)
+    else:
+        loss_vertex, _ = train_ops.smooth_l1_loss_vertex(layers["vertex_pred"], vertex_targets, vertex_weights)
     out = dict(loss_cls=loss_cls, loss_vertex=vertex_w * loss_vertex)
     total = out["loss_cls"] + out["loss_vertex"]
     if net.pose_reg:

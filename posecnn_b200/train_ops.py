@@ -67,3 +67,21 @@ def smooth_l1_loss_vertex(vertex_pred, vertex_targets, vertex_weights, sigma=1.0
     check(lib().pcnn_smooth_l1_vertex_fwd(ptr(p), ptr(t), ptr(w), ctypes.c_size_t(p.numel()), f32(sigma), ptr(out), f32(upstream),
                                           ptr(grad), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
     return (out[0:1], out[1:2], grad) if want_grad else (out[0:1], out[1:2])
+
+
+def vertex_loss_from_centers(vertex_pred, im_label, centers, w_inside=1.0, sigma=1.0, want_grad=False, upstream=1.0):
+    """smooth_l1_loss_vertex(vertex_pred, *generate_vertex_targets(im_label, centers, w_inside)) in one pass that never
+    builds the target / weight tensors.  Returns (loss [1], sum of weights [1][, grad wrt vertex_pred])."""
+    p = require_cuda("vertex_pred", vertex_pred, torch.float32, 4)
+    lab = require_cuda("im_label", im_label, torch.int32, 3)
+    cen = require_cuda("centers", centers, torch.float32, 3)
+    B, H, W = lab.shape
+    C = cen.shape[1]
+    if tuple(p.shape) != (B, H, W, 3 * C) or cen.shape[0] != B or cen.shape[2] != 3:
+        raise ValueError("vertex_pred must be [B,H,W,3C] and centers [B,C,3]")
+    out = torch.empty((2,), dtype=torch.float32, device=p.device)
+    grad = torch.empty_like(p) if want_grad else None
+    ws = _workspace(p.device)
+    check(lib().pcnn_vertex_loss_fused_fwd(ptr(p), ptr(lab), ptr(cen), B, H, W, C, f32(w_inside), f32(sigma), ptr(out), f32(upstream),
+                                           ptr(grad), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    return (out[0:1], out[1:2], grad) if want_grad else (out[0:1], out[1:2])

@@ -146,3 +146,30 @@ def test_training_loss_heads_compose(cuda):
     assert abs(float(losses["loss_pose"].item()) - float(want_p[0])) <= 1e-4 * max(abs(float(want_p[0])), 1e-6)
     total = float(losses["loss_cls"].item()) + float(losses["loss_vertex"].item()) + float(losses["loss_pose"].item())
     assert abs(float(losses["loss"].item()) - total) <= 1e-5 * abs(total)
+
+
+def test_vertex_loss_fused_equals_materialised(cuda):
+    """The fused vertex loss (labels + centres in, no target / weight tensors) == smooth L1 on the materialised targets,
+    forward and gradient, at full frame size."""
+    from posecnn_b200 import synth, train_ops
+    sc = synth.make_scene(batch=2, height=480, width=640, num_classes=22, seed=77)
+    label = sc["label"]
+    rng = np.random.default_rng(2)
+    centers = np.zeros((2, 22, 3), np.float32)
+    for b in range(2):
+        for c in np.unique(label[b]):
+            if c > 0:
+                ys, xs = np.where(label[b] == c)
+                centers[b, c] = (xs.mean() + rng.normal(), ys.mean() + rng.normal(), rng.uniform(0.5, 1.5))
+    centers[0, int(np.unique(label[0])[1]), 2] = 0.0                  # one labelled class not listed
+    pred = T(sc["vertex"], cuda) + 0.3 * torch.randn(sc["vertex"].shape, device=cuda)
+    lab, cen = T(label, cuda), T(centers, cuda)
+    for sigma in (1.0, 2.5):
+        vt, vw = train_ops.generate_vertex_targets(lab, cen, 10.0)
+        l0, w0, g0 = train_ops.smooth_l1_loss_vertex(pred, vt, vw, sigma, want_grad=True, upstream=0.7)
+        l1, w1, g1 = train_ops.vertex_loss_from_centers(pred, lab, cen, 10.0, sigma, want_grad=True, upstream=0.7)
+        assert float(w0.item()) == float(w1.item()) > 0
+        assert abs(float(l0.item()) - float(l1.item())) <= 1e-6 * abs(float(l0.item()))
+        assert torch.equal(g0, g1)
+        want, _ = oracle.smooth_l1_loss_vertex(to_np(pred), to_np(vt), to_np(vw), sigma)
+        assert abs(float(l1.item()) - want) <= 1e-5 * abs(want)
