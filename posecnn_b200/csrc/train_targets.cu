@@ -21,46 +21,6 @@ constexpr int kLossBlocks = kNumSMs * 4;
 constexpr int kLossThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
-// vertex targets: thread = one channel pair (float2) of one pixel; consecutive lanes -> consecutive pairs
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_vertex_targets(const int* __restrict__ label, const float* __restrict__ centers /*[B,C,3] cx, cy, z (z <= 0: absent)*/,
-                 int HW, int W, int C, float w_inside, unsigned total_pairs, float* __restrict__ targets, float* __restrict__ weights)
-{
-    const int P2 = 3 * C / 2 + (3 * C & 1);   // pairs per pixel (3C even in practice; odd tail handled below)
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_pairs; idx += gridDim.x * blockDim.x) {
-        const unsigned pix = idx / P2;
-        const int pr = idx - pix * P2;
-        const int b = pix / HW, p = pix - b * HW;
-        const int l = __ldg(label + pix);
-        float t[2] = {0.f, 0.f}, w[2] = {0.f, 0.f};
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int ch = 2 * pr + e;
-            if (ch >= 3 * C) continue;
-            const int cls = ch / 3, comp = ch - 3 * cls;
-            if (cls != l || l <= 0 || l >= C) continue;
-            const float* cen = centers + ((size_t)b * C + cls) * 3;
-            const float z = cen[2];
-            if (!(z > 0.f)) continue;                     // class not in cls_indexes (minibatch.py:583-584)
-            // numpy: float32 centre minus int64 pixel coordinates -> float64 arithmetic, stored as float32 (:589-597)
-            const double dx = (double)cen[0] - (double)(p % W), dy = (double)cen[1] - (double)(p / W);
-            const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
-            t[e] = comp == 0 ? (float)(dx / nrm) : (comp == 1 ? (float)(dy / nrm) : (float)log((double)z));
-            w[e] = w_inside;
-        }
-        const size_t o = (size_t)pix * 3 * C + 2 * pr;
-        if (2 * pr + 1 < 3 * C && ((3 * C) & 1) == 0) {
-            *reinterpret_cast<float2*>(targets + o) = make_float2(t[0], t[1]);
-            *reinterpret_cast<float2*>(weights + o) = make_float2(w[0], w[1]);
-        } else {
-            targets[o] = t[0]; weights[o] = w[0];
-            if (2 * pr + 1 < 3 * C) { targets[o + 1] = t[1]; weights[o + 1] = w[1]; }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // deterministic two-value reduction: per-CTA partials, last CTA sums them in index order
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_reduce2(double& a, double& b, double* sh /*[2 * warps]*/)
@@ -206,6 +166,22 @@ __device__ __forceinline__ bool pixel_targets(const int* __restrict__ label, con
     return true;
 }
 
+// materialised targets / weights (drop-in for the data layer's blobs): the tensors are >97 % zeros, so they are
+// cleared with two memset nodes and only the three channels of each labelled pixel's own class are written
+__global__ void __launch_bounds__(256)
+k_vertex_targets_sparse(const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW, int W, int C, float w_inside,
+                        float* __restrict__ targets, float* __restrict__ weights)
+{
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        int cls;
+        float t[3];
+        if (!pixel_targets(label, centers, pix, HW, W, C, cls, t)) continue;
+        const size_t o = (size_t)pix * 3 * C + 3 * cls;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { targets[o + k] = t[k]; weights[o + k] = w_inside; }
+    }
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 k_vertex_loss_fused(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW,
                     int W, int C, float w_inside, float sigma2, double* __restrict__ partial, unsigned* __restrict__ ticket,
@@ -289,11 +265,12 @@ extern "C" int pcnn_vertex_targets_fwd(const int32_t* label, const float* center
 {
     PCNN_REQUIRE(label && centers && targets && weights, "vertex_targets: NULL tensor pointer");
     PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1, "vertex_targets: bad shape");
-    const int P2 = 3 * C / 2 + (3 * C & 1);
-    const unsigned long long total = (unsigned long long)B * H * W * P2;
-    PCNN_REQUIRE(total < 0xffffffffULL, "vertex_targets: too many elements for 32-bit indexing");
-    int blocks = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)kNumSMs * 32);
-    k_vertex_targets<<<blocks, 256, 0, (cudaStream_t)stream>>>(label, centers, H * W, W, C, w_inside, (unsigned)total, targets, weights);
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "vertex_targets: too many pixels");
+    const unsigned npix = (unsigned)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(targets, 0, sizeof(float) * (size_t)npix * 3 * C, st);
+    cudaMemsetAsync(weights, 0, sizeof(float) * (size_t)npix * 3 * C, st);
+    k_vertex_targets_sparse<<<kNumSMs * 16, 256, 0, st>>>(label, centers, npix, H * W, W, C, w_inside, targets, weights);
     return check_launch("vertex_targets");
 }
 
