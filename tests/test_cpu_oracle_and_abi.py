@@ -260,3 +260,23 @@ def test_bench_reference_arm_prints_one_json_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["value"] == d["value"]
+
+
+def test_reference_import_paths_resolve():
+    """Every op module lib/networks/network.py:6-26 imports exists under posecnn_b200/ with the reference's symbol names;
+    the baseline-only CPU Houghvoting op fails loudly instead of falling back."""
+    import importlib
+    want = {"hough_voting_gpu_layer.hough_voting_gpu_op": ["hough_voting_gpu", "hough_voting_gpu_grad"],
+            "hough_voting_layer.hough_voting_op": ["hough_voting", "hough_voting_grad"],
+            "roi_pooling_layer.roi_pooling_op": ["roi_pool", "roi_pool_grad"],
+            "hard_label_layer.hard_label_op": ["hard_label", "hard_label_grad"],
+            "backprojecting_layer.backprojecting_op": ["backproject", "backproject_grad"],
+            "projecting_layer.projecting_op": ["project", "project_grad"],
+            "average_distance_loss.average_distance_loss_op": ["average_distance_loss", "average_distance_loss_grad"]}
+    for mod, names in want.items():
+        m = importlib.import_module("posecnn_b200." + mod)
+        for n in names:
+            assert callable(getattr(m, n)), (mod, n)
+    from posecnn_b200.hough_voting_layer import hough_voting_op
+    with pytest.raises(NotImplementedError):
+        hough_voting_op.hough_voting(None, None, None, None, None, 0)
