@@ -13,6 +13,16 @@ def hwio_to_tc(weights_hwio: torch.Tensor) -> torch.Tensor:
     return weights_hwio.permute(3, 0, 1, 2).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
 
 
+def hwio_to_tc_dgrad(weights_hwio: torch.Tensor) -> torch.Tensor:
+    """Weights for the INPUT-gradient pass of a SAME / stride-1 convolution, in the layout `conv_bf16` consumes:
+    d x = conv(d y, W') with W'[r, s, co, ci] = W[k-1-r, k-1-s, ci, co] (taps flipped, channels transposed), so the
+    backward-data pass of every trunk layer is the forward tensor-core kernel on these weights (zero bias, no ReLU;
+    the ReLU mask of the layer below multiplies the result).  Returns [Cin][k*k*Cout] bf16."""
+    kh, kw, ci, co = weights_hwio.shape
+    flipped = torch.flip(weights_hwio, dims=(0, 1)).permute(0, 1, 3, 2).contiguous()      # [kh, kw, co, ci] = HWIO of the dgrad conv
+    return hwio_to_tc(flipped)
+
+
 def conv_bf16(x: torch.Tensor, w_tc: torch.Tensor, bias: torch.Tensor, ksize: int, relu: bool, block_n: int = 0,
               out: torch.Tensor | None = None) -> torch.Tensor:
     """x [B,H,W,Cin] bf16, w_tc [Cout, k*k*Cin] bf16, bias [Cout] f32 -> [B,H,W,Cout] bf16."""

@@ -280,3 +280,25 @@ def test_reference_import_paths_resolve():
     from posecnn_b200.hough_voting_layer import hough_voting_op
     with pytest.raises(NotImplementedError):
         hough_voting_op.hough_voting(None, None, None, None, None, 0)
+
+
+def test_dgrad_weight_transform_matches_autograd():
+    """Host logic for the backward-data pass (DESIGN.md plan item 3): the forward kernel on tap-flipped, channel-transposed
+    weights computes d x.  Checked on CPU: F.conv2d with the transformed weights == torch.autograd of the forward conv."""
+    import torch
+    import torch.nn.functional as F
+    from posecnn_b200 import conv
+    g = torch.Generator().manual_seed(0)
+    for k, ci, co in ((3, 8, 16), (1, 16, 8)):
+        w = torch.randn((k, k, ci, co), generator=g)                       # HWIO, network.py:166-170
+        x = torch.randn((2, ci, 9, 11), generator=g, requires_grad=True)
+        y = F.conv2d(x, w.permute(3, 2, 0, 1), padding=k // 2)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        wt = conv.hwio_to_tc_dgrad(w).float()                               # [Cin][k*k*Cout], K order (tap, cout)
+        assert wt.shape == (ci, k * k * co)
+        w_d = wt.reshape(ci, k, k, co).permute(0, 3, 1, 2)                   # OIHW of the dgrad convolution
+        dx = F.conv2d(dy.to(torch.bfloat16).float(), w_d, padding=k // 2)    # what conv_bf16(dy, wt, 0, k, relu=False) computes
+        assert torch.allclose(dx, x.grad, rtol=2e-2, atol=2e-2 * x.grad.abs().max().item())
+        exact = F.conv2d(dy, torch.flip(w, (0, 1)).permute(2, 3, 0, 1), padding=k // 2)   # same transform in fp32: exact
+        assert torch.allclose(exact, x.grad, rtol=1e-4, atol=1e-4)
