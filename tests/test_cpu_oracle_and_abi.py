@@ -302,3 +302,25 @@ def test_dgrad_weight_transform_matches_autograd():
         assert torch.allclose(dx, x.grad, rtol=2e-2, atol=2e-2 * x.grad.abs().max().item())
         exact = F.conv2d(dy, torch.flip(w, (0, 1)).permute(2, 3, 0, 1), padding=k // 2)   # same transform in fp32: exact
         assert torch.allclose(exact, x.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_blob_helpers():
+    """Host halves of the input pre-processing (lib/utils/blob.py:48-71, lib/fcn/test.py:72-76)."""
+    from posecnn_b200.utils import blob
+    rng = np.random.default_rng(0)
+    im = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    p = blob.pad_im(im, 16)
+    assert p.shape == (48, 64, 3) and (p[:37, :53] == im).all() and not p[37:].any() and not p[:, 53:].any()
+    want = np.pad(im, ((0, 11), (0, 11), (0, 0)), "constant", constant_values=0)          # what np.lib.pad does in the reference
+    np.testing.assert_array_equal(p, want)
+    assert blob.pad_im(im[:, :, 0], 16, value=7).shape == (48, 64) and blob.pad_im(p, 16).shape == p.shape
+    assert blob.unpad_im(p, 16).shape == p.shape                                             # the reference's unpad: no-op on padded sizes
+    cb = blob.color_blob([im, im[:20, :30]])
+    assert cb.shape == (2, 48, 64, 3) and cb.dtype == np.uint8 and (cb[1, :20, :30] == im[:20, :30]).all()
+    assert np.abs(cb[0, 40, 60].astype(np.float32) - blob.PIXEL_MEANS).max() <= 0.5          # padded pixels ~ zero after mean subtraction
+    d = rng.integers(0, 6000, (37, 53)).astype(np.uint16)
+    db = blob.depth_blob([d])
+    ref = np.clip(d.astype(np.float32) / 2000.0, 0, 1) * 255
+    ref = np.tile(ref[:, :, np.newaxis], (1, 1, 3)) - blob.PIXEL_MEANS                       # test.py:72-76
+    np.testing.assert_array_equal(db[0, :37, :53], ref.astype(np.float32))
+    assert db.shape == (1, 48, 64, 3) and not db[0, 37:].any()
