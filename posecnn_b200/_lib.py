@@ -49,12 +49,24 @@ def f32(x: float):
     return ctypes.c_float(float(x))
 
 
-def workspace(tag: str, nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-(tag, device) scratch buffer; stream-ordered reuse on the current stream."""
-    key = (tag, str(device))
+def workspace(tag: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+    """Scratch buffer for one native call, stream-ordered on the current stream.
+
+    Eager calls: grow-only cache keyed by (tag, device, stream) — two streams never share a scratch buffer, and a
+    buffer is only ever replaced by a larger one for the SAME stream (the old one returns to the caching allocator,
+    which is stream-ordered for that stream).  Under CUDA-graph capture the buffer is allocated fresh from the graph's
+    private memory pool and NOT cached: it belongs to the graph for the graph's lifetime, so a later eager call that
+    needs a larger scratch can never free (or scribble over) memory a captured graph still replays into.
+    `zero=True`: the buffer is zero-filled when it is created (kernels that re-arm their own tickets)."""
+    device = torch.device(device)
+    n = max(int(nbytes), 256)
+    make = torch.zeros if zero else torch.empty
+    if torch.cuda.is_current_stream_capturing():
+        return make(n, dtype=torch.uint8, device=device)
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    if buf is None or buf.numel() < n:
+        buf = make(n, dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
 

@@ -176,8 +176,7 @@ extern "C" int pcnn_average_distance_fwd(const float* prediction, const float* t
     if (N == 0) return PCNN_OK;
     size_t smem = sizeof(float4) * (size_t)P;
     PCNN_REQUIRE(smem <= 200 * 1024, "average_distance: P = %d model points exceed the shared-memory staging", P);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_average_distance, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    PCNN_SMEM_OPTIN(k_average_distance, 200 * 1024, "average_distance");
     k_average_distance<<<N, kAdThreads, smem, st>>>(prediction, target, weight, point, symmetry, N, C, P, margin, loss,
                                                     bottom_diff, (float*)((char*)workspace + 256), (unsigned*)workspace);
     return check_launch("average_distance_fwd");

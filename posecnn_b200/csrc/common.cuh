@@ -9,6 +9,13 @@
 namespace pcnn {
 
 void set_error(const char* fmt, ...);
+// > 48 KB dynamic shared memory opt-in, once per (kernel, device); returns PCNN_OK or PCNN_E_CUDA (api.cu)
+int smem_optin(const void* func, int bytes, const char* what);
+#define PCNN_SMEM_OPTIN(kernel, bytes, what)                                        \
+    do {                                                                            \
+        int rc_ = pcnn::smem_optin((const void*)(kernel), (int)(bytes), what);      \
+        if (rc_) return rc_;                                                        \
+    } while (0)
 
 inline int check_launch(const char* what)
 {

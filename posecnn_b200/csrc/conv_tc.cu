@@ -1100,12 +1100,7 @@ static int launch_conv(const CUtensorMap& mi, const CUtensorMap& mw, const CUten
                        cudaStream_t st)
 {
     using Plan = SmemPlan<BN>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
-        if (e != cudaSuccess) { set_error("conv_tc<%d>: cannot reserve %d B of shared memory: %s", BN, Plan::kTotal, cudaGetErrorString(e)); return PCNN_E_CUDA; }
-        attr = true;
-    }
+    PCNN_SMEM_OPTIN(k_conv_tc<BN>, Plan::kTotal, "conv_tc");
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     k_conv_tc<BN><<<grid, kThreadsConv, Plan::kTotal, st>>>(mi, mw, mo, p);
     return check_launch("conv_tc");
@@ -1116,12 +1111,7 @@ static int launch_conv_row2(const CUtensorMap& mi, const CUtensorMap& mw, const 
                             cudaStream_t st)
 {
     using Plan = RowPlan<BN, RESB>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_row2<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
-        if (e != cudaSuccess) { set_error("conv_row2<%d>: cannot reserve %d B of shared memory: %s", BN, Plan::kTotal, cudaGetErrorString(e)); return PCNN_E_CUDA; }
-        attr = true;
-    }
+    PCNN_SMEM_OPTIN((k_conv_row2<BN, RESB>), Plan::kTotal, "conv_row2");
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (RESB) grid = grid / p.n_tiles_n * p.n_tiles_n;  // every CTA owns one N tile
     k_conv_row2<BN, RESB><<<grid, kThreadsConv, Plan::kTotal, st>>>(mi, mw, mo, p);
@@ -1290,12 +1280,8 @@ extern "C" int pcnn_conv1_fused_tc(const void* in, int in_is_u8, const float* me
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = p.total_tiles < sms ? p.total_tiles : sms;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_conv1_tc<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
-        cudaFuncSetAttribute(k_conv1_tc<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1Smem);
-        attr = true;
-    }
+    PCNN_SMEM_OPTIN(k_conv1_tc<unsigned char>, kC1Smem, "conv1_tc<u8>");
+    PCNN_SMEM_OPTIN(k_conv1_tc<float>, kC1Smem, "conv1_tc<f32>");
     if (in_is_u8) k_conv1_tc<unsigned char><<<grid, kC1Threads, kC1Smem, st>>>((const unsigned char*)in, mw, mo, p, m0, m1, m2);
     else k_conv1_tc<float><<<grid, kC1Threads, kC1Smem, st>>>((const float*)in, mw, mo, p, m0, m1, m2);
     return check_launch("conv1_fused_tc");

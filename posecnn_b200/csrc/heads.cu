@@ -385,8 +385,7 @@ extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const v
     size_t smem = sizeof(float) * (folded ? (size_t)Cs * C + (size_t)kLrWarps * kLrPix * Cs
                                           : (size_t)Cs * C + (size_t)Cv * 3 * C + (size_t)kLrWarps * kLrPix * (Cs + Cv));
     PCNN_REQUIRE(smem <= 200 * 1024, "lowres_heads: weights do not fit shared memory");
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_lowres_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    PCNN_SMEM_OPTIN(k_lowres_heads, 200 * 1024, "lowres_heads");
     PCNN_REQUIRE((long long)B * h * w < 0x7fffffffLL, "lowres_heads: too many pixels");
     size_t npix = (size_t)B * h * w;
     int blocks = (int)std::min<size_t>((npix + kLrPix * kLrWarps - 1) / (kLrPix * kLrWarps), (size_t)kNumSMs * (folded ? 8 : 2));
@@ -407,12 +406,8 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
     size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: segment does not fit shared memory (C = %d)", C);
     dim3 grid(8 * h, B, (w + seg_cells - 1) / seg_cells);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_up8_heads<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_up8_heads<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
-    }
+    PCNN_SMEM_OPTIN(k_up8_heads<0>, 200 * 1024, "up8_heads<0>");
+    PCNN_SMEM_OPTIN(k_up8_heads<22>, 200 * 1024, "up8_heads<22>");
     if (C == 22)   // the YCB / LOV class count (lov_color_2d.yml:14): compile-time strides
         k_up8_heads<22><<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, bias_score, bias_vertex, h, w, C, seg_cells, label, vertex,
                                                                    prob, score);

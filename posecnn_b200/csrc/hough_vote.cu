@@ -989,11 +989,7 @@ static int run_front(const Layout& L, char* ws, const int32_t* label, const floa
                                               img_count, samples, L.samp_cap, bbox);
     k_worklist<<<1, 1024, 0, st>>>(B, C, L.R, L.nbands, img_count, slot_cls, cls_nsamp, bbox, work, work_ctr);
     size_t smem = sizeof(int) * (size_t)L.R * (W + 3);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        attr_set = true;
-    }
+    PCNN_SMEM_OPTIN(k_vote, 110 * 1024, "hough k_vote");
     k_vote<<<4 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, slot_cls, cls_nsamp, cls_soff, bbox,
                                                 samples, L.samp_cap, work, work_ctr, band_res, votes_out);
     return check_launch("hough front kernels");

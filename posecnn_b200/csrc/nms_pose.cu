@@ -158,8 +158,7 @@ extern "C" int pcnn_nms_pose_fwd(const float* rois, const float* poses_init, con
     PCNN_REQUIRE(num_rois_dev || (num_rows >= 0 && num_rows <= capacity), "nms_pose: num_rows %d outside [0, capacity]", num_rows);
     PCNN_REQUIRE(!poses_pred || num_classes >= 1, "nms_pose: poses_pred needs num_classes >= 1");
     size_t smem = (size_t)capacity * (sizeof(NmsBox) + 2 * sizeof(int) + 1) + (size_t)(capacity + 1) * sizeof(int) + 16;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_nms_pose, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+    PCNN_SMEM_OPTIN(k_nms_pose, 100 * 1024, "nms_pose");
     PCNN_REQUIRE(smem <= 100 * 1024, "nms_pose: capacity %d does not fit shared memory", capacity);
     k_nms_pose<<<1, kNmsThreads, smem, (cudaStream_t)stream>>>(rois, poses_init, poses_pred, num_rois_dev, num_rows, capacity,
                                                                num_classes, thresh, per_image, keep, out_rois, out_poses, num_keep);

@@ -1,0 +1,20 @@
+"""Gradientreversal — import stub for lib/gradient_reversal_layer/gradient_reversal_op.py:1-7.
+
+`lib/networks/network.py:6-26` imports this module unconditionally, so it must exist for the reference's network code
+to import against this package ("stub modules for the other ops").  The op is OUTSIDE the hot path
+this package implements (DESIGN.md §1 "out of scope"); the symbols exist, calling them fails loudly.
+There is no CPU or library fallback.
+"""
+from __future__ import annotations
+
+
+def _out_of_scope(name):
+    def op(*args, **kwargs):
+        raise NotImplementedError("%s (%s) is outside the PoseCNN inference hot path posecnn_b200 implements "
+                                  "(SURVEY.md §8); the vgg16_convs network never calls it" % (name, "Gradientreversal"))
+    op.__name__ = name
+    return op
+
+
+gradient_reversal = _out_of_scope("gradient_reversal")
+gradient_reversal_grad = _out_of_scope("gradient_reversal_grad")

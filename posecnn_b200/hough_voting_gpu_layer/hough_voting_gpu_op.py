@@ -64,15 +64,31 @@ def hough_voting_gpu_capacity(bottom_label, bottom_vertex, bottom_extents, botto
     return box, pose, target, weight, domain, num_rois, status
 
 
+def check_status(overflow_bits: int, mismatches: int):
+    """The device status word of pcnn_hough_vote_fwd (include/posecnn_b200.h): bit 0 of [0] = the per-image candidate
+    list of threshold mode overflowed (which maxima survive then depends on atomic arrival order, like the reference's
+    own `atomicAdd` compaction, .cu.cc:377 — the canonical order is lost); [1] = selected cells whose interval-scan
+    vote differs from the exact per-cell recount (the reported vote is always the recount)."""
+    import warnings
+    if overflow_bits & 1:
+        warnings.warn("Houghvotinggpu: more local maxima than the candidate capacity (4096 per image); the kept subset is "
+                      "not in canonical order", RuntimeWarning)
+    if mismatches:
+        warnings.warn("Houghvotinggpu: %d selected cells sit within rounding distance of the vote predicate's threshold "
+                      "(interval scan != per-cell recount; the recount is reported)" % mismatches, RuntimeWarning)
+
+
 def hough_voting_gpu(bottom_label, bottom_vertex, bottom_extents, bottom_meta_data, bottom_gt, is_train,
                      threshold_vote, threshold_percentage, skip_pixels, name=None):
     """Same positional order as the TF op.  Output row count is data dependent and always
     >= 1 (dummy all-zero row, hough_voting_gpu_op.cc:379-383), hence one host read of the
     device row counter, as in the reference (copy_num_rois, .cu.cc:591-594)."""
-    box, pose, target, weight, domain, num_rois, _ = hough_voting_gpu_capacity(
+    box, pose, target, weight, domain, num_rois, status = hough_voting_gpu_capacity(
         bottom_label, bottom_vertex, bottom_extents, bottom_meta_data, bottom_gt, is_train, threshold_vote,
         threshold_percentage, skip_pixels)
-    n = max(1, int(num_rois.item()))
+    host = torch.cat([num_rois, status[:2]]).tolist()     # the one host read the data-dependent shape requires
+    n = max(1, host[0])
+    check_status(host[1], host[2])
     return box[:n], pose[:n], target[:n], weight[:n], domain[:n]
 
 

@@ -248,6 +248,7 @@ class vgg16_convs:
         cap_rows = max(1, min(box.shape[0], (128 // B) * B * (9 if self.is_train else 1)))
         rois = box[:cap_rows]
         L["rois_capacity"], L["num_rois"] = rois, num_rois
+        L["hough_status"] = status      # device status word (overflow bit, scan/recount mismatches); read in the sync path
         L["poses_init"], L["poses_target"], L["poses_weight"] = pose[:cap_rows], target[:cap_rows], weight[:cap_rows]
         if self.pose_reg:
             p5, _ = roi_pooling_op.roi_pool(c5, rois, 7, 7, 1.0 / 16.0, 0)
@@ -263,7 +264,9 @@ class vgg16_convs:
                                                                    self.nms_thresh, per_image=True, num_classes=C)
             L["detections_keep"], L["detections_rois"], L["detections_poses"], L["num_detections"] = keep, d_rois, d_poses, d_n
         if sync_rois:
-            n = max(1, int(num_rois.item()))  # the one host read the op's data-dependent shape requires
+            host = torch.cat([num_rois, status[:2]]).tolist()  # the one host read the op's data-dependent shape requires
+            n = max(1, host[0])
+            hough_voting_gpu_op.check_status(host[1], host[2])
             L["rois"] = rois[:n]
             for k in ("poses_init", "poses_target", "poses_weight"):
                 L[k] = L[k][:n]
@@ -280,6 +283,10 @@ def training_losses(net: vgg16_convs, layers: dict, gt_label_2d, vertex_targets,
       loss_vertex = VERTEX_W * smooth_l1_loss_vertex(vertex_pred, vertex_targets, vertex_weights)
                     (vertex_targets=None + centers [B,C,3]: the fused kernel that derives targets from gt_label_2d / centers)
       loss_pose   = Averagedistance(l2_normalize(poses_tanh * poses_weight), poses_target, poses_weight, points, symmetry)
+    This is the keep_prob = 1.0 graph: the reference TRAINS with dropout 0.5 after add_score / add_score_vertex / fc6 / fc7
+    (lib/fcn/train.py:404-434); the folded vertex head and the commuted bilinear heads are algebraically exact only
+    without that dropout, so the losses equal the reference's at keep_prob = 1 (SURVEY.md App. A.7 makes the same
+    restriction for any parity run: random masks cannot be compared).
     Returns the three losses and their sum as [1] tensors (no host synchronisation)."""
     from .. import train_ops
     from ..average_distance_loss import average_distance_loss_op
@@ -296,6 +303,14 @@ def training_losses(net: vgg16_convs, layers: dict, gt_label_2d, vertex_targets,
         pred = mul / mul.pow(2).sum(1, keepdim=True).clamp(min=1e-12).sqrt()            # tf.nn.l2_normalize(dim=1)
         loss_pose, pose_diff = average_distance_loss_op.average_distance_loss(pred.contiguous(), layers["poses_target"].contiguous(),
                                                                               layers["poses_weight"].contiguous(), points, symmetry, margin)
+        # Averagedistance normalises by N = the number of ROI rows it is given (.cu.cc:181,196).  In the graph-friendly
+        # mode (forward(sync_rois=False)) those are capacity buffers whose padding rows have weight 0 but still count in
+        # N; rescale by capacity / max(num_rois, 1) with the DEVICE row count so that loss and gradient equal the
+        # reference's on the real rows, without a host synchronisation.
+        cap_rows = layers["poses_tanh"].shape[0]
+        if "num_rois" in layers and "rois" not in layers:
+            fix = float(cap_rows) / layers["num_rois"].clamp(min=1).to(torch.float32)
+            loss_pose, pose_diff = loss_pose * fix, pose_diff * fix
         out.update(loss_pose=loss_pose, poses_pred=pred, poses_pred_diff=pose_diff)
         total = total + loss_pose
     out["loss"] = total

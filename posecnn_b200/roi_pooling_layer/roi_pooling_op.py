@@ -40,13 +40,16 @@ def roi_pool(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scal
 
 def roi_pool_grad(bottom_data, bottom_rois, argmax, grad, pooled_height, pooled_width, spatial_scale, pool_channel=0,
                   name=None):
-    data = require_cuda("bottom_data", bottom_data, torch.float32, 4)
+    # bottom_data only supplies the shape (RoiPoolGrad reads no feature values, roi_pooling_op_gpu.cu.cc:134-229): it
+    # may be the trunk's bf16 activation; the gradient is float32 like the reference's
+    if not (isinstance(bottom_data, torch.Tensor) and bottom_data.is_cuda and bottom_data.dim() == 4):
+        raise RuntimeError("bottom_data must be a 4-dimensional CUDA tensor (posecnn_b200 has no CPU path)")
     rois = require_cuda("bottom_rois", bottom_rois, torch.float32, 2)
     argmax = require_cuda("argmax", argmax, torch.int32, 4)
     grad = require_cuda("grad", grad, torch.float32, 4)
-    B, H, W, C = data.shape
+    B, H, W, C = bottom_data.shape
     N, cr = rois.shape
-    out = torch.empty_like(data)
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=bottom_data.device)
     check(lib().pcnn_roi_pool_bwd(ptr(grad), ptr(argmax), ptr(rois), B, N, cr, H, W, C, int(pooled_height),
                                   int(pooled_width), f32(spatial_scale), int(pool_channel), ptr(out), stream()))
     return out

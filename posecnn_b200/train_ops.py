@@ -10,18 +10,12 @@ import ctypes
 
 import torch
 
-from ._lib import check, f32, lib, ptr, require_cuda, stream
-
-_WS = {}
-
+from ._lib import check, f32, lib, ptr, require_cuda, stream, workspace
 
 def _workspace(device):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    if key not in _WS:
-        n = ctypes.c_size_t(0)
-        check(lib().pcnn_train_loss_workspace_bytes(ctypes.byref(n)))
-        _WS[key] = torch.zeros(int(n.value), dtype=torch.uint8, device=device)   # zero once: the kernels re-arm the ticket
-    return _WS[key]
+    n = ctypes.c_size_t(0)
+    check(lib().pcnn_train_loss_workspace_bytes(ctypes.byref(n)))
+    return workspace("train_loss", int(n.value), device, zero=True)   # zero once: the kernels re-arm the ticket
 
 
 def generate_vertex_targets(im_label, centers, w_inside=1.0):

@@ -1,0 +1,1 @@
+"""Import stub: out of the hot path; see the op module."""
