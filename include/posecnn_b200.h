@@ -65,6 +65,22 @@ int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, const float* 
                         float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
                         float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
                         int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Extended form of pcnn_hough_vote_fwd for the two things a caller that owns the whole pipeline needs:
+ *  (1) image shards of a larger batch: this call holds images [batch_offset, batch_offset + B) of a
+ *      batch of batch_global images; the ROI budget is MAX_ROI / batch_global per image (hough_voting_gpu_op.cu.cc:733,
+ *      applied to the batch the reference op would see), top_box[:,0] and the gt match use GLOBAL batch indices, so
+ *      the concatenation of the shards' rows in rank order equals the single-call result on the whole batch;
+ *  (2) vertex == NULL: the sampled pixels' (dx, dy, log z) are computed on demand from the network's 1/8-resolution head
+ *      tensor `lowres` [B,H/8,W/8,4C] (pcnn_lowres_heads) + bias_vertex [3C] with pcnn_up8_heads' own operation
+ *      sequence — bit-identical to reading the dense vertex_pred, which then never has to be written (2.6 GB per
+ *      batch of 32).  With vertex != NULL, lowres / bias_vertex are ignored. */
+int pcnn_hough_vote_fwd_ex(const int32_t* label, const float* vertex, const float* lowres, const float* bias_vertex,
+                           const float* extents, const float* meta, const float* gt, int B, int batch_global,
+                           int batch_offset, int H, int W, int C, int num_gt, int num_meta, int is_train,
+                           float inlier_threshold, int label_threshold, float threshold_vote,
+                           float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
+                           float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
+                           int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 /* Debug / parity helper: dense vote planes [B,C,H,W] f32 (0 for classes that did not vote),
  * computed by the same interval-scan kernels.  Used by tests to compare with the oracle. */
 int pcnn_hough_vote_planes(const int32_t* label, const float* vertex, const float* extents, const float* meta,
@@ -168,7 +184,31 @@ int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_host, void* 
  * weights [64][64] bf16 in the K order tap*3 + c (zero padded), bias [64] -> out [B,H,W,64] bf16 */
 int pcnn_conv1_fused_tc(const void* in, int in_is_u8, const float* mean3_host, const void* weights_bf16,
                         const float* bias, void* out_bf16, int B, int H, int W, int relu, void* stream);
+/* conv1_1_p of the RGB-D network on a RAW depth image: depth [B,H,W] f32 (sensor units); the depth blob
+ * clip(d / 2000, 0, 1) * 255 tiled x3 - PIXEL_MEANS (lib/fcn/test.py:70-76) is formed in the loader, float32 like numpy */
+int pcnn_conv1_depth_fused_tc(const float* depth, const float* mean3_host, const void* weights_bf16, const float* bias,
+                              void* out_bf16, int B, int H, int W, int relu, void* stream);
 int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pose-regression head (networks/vgg16_convs.py:177-197, Network.fc networks/network.py:392-422, tanh :436-438) on own
+ * kernels (csrc/fc_tc.cu); inference path (no argmax, no gradients).
+ *  pcnn_roi_pool_pair_bf16  pool_score = RoiPool(conv5_3, scale5) + RoiPool(conv4_3, scale4) with the RoiPool rule of
+ *      roi_pooling_layer/roi_pooling_op_gpu.cu.cc:19-101, added in fp32 and written as the bf16 fc6 operand
+ *      [num_rois, pooled_h*pooled_w*C] in (h, w, c) order.  f5 [B,H5,W5,C], f4 [B,H4,W4,C] bf16 NHWC; rois
+ *      [num_rois, roi_stride] f32 rows [batch, cls, x1,y1,x2,y2,...]; the image index is rois[:,0] - batch_offset
+ *      (image shards carry global batch indices); an index outside [0, B) pools nothing (zeros).
+ *  pcnn_fc_bf16_tc          out = act(A[M,K] @ W[N,K]^T + bias): tcgen05 GEMM, BF16 operands, FP32 accumulation, split-K
+ *      over the grid with a fixed-order reduction (deterministic); A, W bf16 row-major with K contiguous, N % 128 == 0,
+ *      K % 64 == 0; rows n_valid..N of W are zero padding; act 0 none / 1 ReLU / 2 tanh; outputs: out_bf16 [M, ld_out]
+ *      (optional) and / or out_f32 [M, n_valid] (optional).  workspace: pcnn_fc_workspace_bytes(M, N, K).
+ */
+int pcnn_roi_pool_pair_bf16(const void* f5_bf16, int H5, int W5, const void* f4_bf16, int H4, int W4, int C, int B,
+                            int batch_offset, const float* rois, int num_rois, int roi_stride, int pooled_h,
+                            int pooled_w, float scale5, float scale4, void* out_bf16, void* stream);
+int pcnn_fc_workspace_bytes(int M, int N, int K, size_t* bytes);
+int pcnn_fc_bf16_tc(const void* a_bf16, const void* w_bf16, const float* bias, int M, int N, int K, int n_valid, int act,
+                    void* out_bf16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * FCN heads after the 1x1 convolutions on conv4_3 / conv5_3 (networks/vgg16_convs.py:128-163):
@@ -186,6 +226,7 @@ int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int 
 int pcnn_lowres_heads(const void* score4, const void* score5, const void* vert4, const void* vert5,
                       const float* w_score, const float* w_vertex, int B, int h, int w, int Cs, int Cv, int C,
                       float* lowres, void* stream);
+/* vertex == NULL: label-only mode (label_2d / prob / score only; see pcnn_hough_vote_fwd_ex for the consumer) */
 int pcnn_up8_heads(const float* lowres, const float* bias_score, const float* bias_vertex, int B, int h, int w,
                    int C, int32_t* label, float* vertex, float* prob, float* score, void* stream);
 /* depthwise bilinear conv2d_transpose (k x k, stride s, SAME) on f32 NHWC — un-fused reference path */

@@ -112,6 +112,32 @@ def timed_baseline(sample_frames=32, threads=None, repeats=5):
                 thread_sweep_ms=sweep)
 
 
+def timed_on_scenes(scenes, repeats=5):
+    """frames/s of the CPU op on GIVEN scenes (the very frames the GPU Hough figures of the same bench run use; dict
+    from posecnn_b200.synth.make_scene).  Same conventions as timed_baseline: the third vertex channel carries z instead of
+    log z (the CPU op's own convention, see _bench_frames), thread count = the fastest of a measured sweep."""
+    ver = scenes["vertex"].copy()
+    ver[..., 2::3] = np.exp(ver[..., 2::3])
+    n = scenes["label"].shape[0]
+    args = (scenes["label"], ver, scenes["extents"], scenes["meta"])
+    threads, sweep = _best_threads(args)
+    hough_voting(*args, threads=threads)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        hough_voting(*args, threads=threads)
+        ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    hough_voting(*args, threads=1)
+    t1 = (time.perf_counter() - t0) / n
+    dt = float(np.median(ts))
+    return dict(value=n / dt, unit="frames/s", cores=threads, kind="port", host_cores=_host_cores(), ms_per_frame=1e3 * dt / n,
+                single_thread_frames_per_s=1.0 / t1, thread_sweep_ms=sweep,
+                sample=f"the same {n} synthetic 640x480x22-class frames x {repeats} runs, CPU hough_voting_layer (RANSAC) restated in "
+                       f"C++ (-O3 -fopenmp), {threads} threads = fastest of the sweep (ms per {n} frames) on {_host_cores()} host cores; "
+                       f"unpinned port (OpenCV / TF absent: cannot be checked against the real op)")
+
+
 def reference_arm(args):
     """`bench.py --impl reference`: the reference's own CPU implementation of the path on host cores (thread count =
     the fastest of a measured sweep; all cores is far from the fastest for this op)."""

@@ -98,3 +98,15 @@ def conv1_fused(x: torch.Tensor, w_tc64: torch.Tensor, bias: torch.Tensor, mean=
     check(lib().pcnn_conv1_fused_tc(ptr(x), int(x.dtype == torch.uint8), m, ptr(w_tc64), ptr(bias), ptr(out), B, H, W,
                                     int(bool(relu)), stream()))
     return out
+
+
+def conv1_depth_fused(depth: torch.Tensor, w_tc64: torch.Tensor, bias: torch.Tensor, mean, relu: bool = True) -> torch.Tensor:
+    """conv1_1_p on a raw depth image: depth [B,H,W] f32 (sensor units) -> [B,H,W,64] bf16; the depth blob of
+    lib/fcn/test.py:70-76 (clip(d / 2000, 0, 1) * 255 tiled x3 - PIXEL_MEANS) is formed inside the kernel's loader."""
+    import ctypes
+    assert depth.is_cuda and depth.is_contiguous() and depth.dtype == torch.float32 and depth.dim() == 3
+    B, H, W = depth.shape
+    out = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=depth.device)
+    m = (ctypes.c_float * 3)(*mean)
+    check(lib().pcnn_conv1_depth_fused_tc(ptr(depth), m, ptr(w_tc64), ptr(bias), ptr(out), B, H, W, int(bool(relu)), stream()))
+    return out

@@ -23,19 +23,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "heads_common.cuh"
 
 namespace pcnn {
-
-// make_deconv_filter (network.py:141-157): f = ceil(k/2), c = (2f - 1 - f%2) / (2f), W[x] = 1 - |x/f - c|
-__host__ __device__ inline float deconv_w(int x, int k)
-{
-    // k = 16: f = 8, c = 15/16; k = 4: f = 2, c = 3/4 (exact in binary floating point)
-    if (k == 16) return 1.f - fabsf((float)x * 0.125f - 0.9375f);
-    if (k == 4) return 1.f - fabsf((float)x * 0.5f - 0.75f);
-    int f = (k + 1) / 2;
-    float c = (2.f * f - 1.f - (float)(f % 2)) / (2.f * f);
-    return 1.f - fabsf((float)x / (float)f - c);
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_lowres_heads: one warp per group of 8 consecutive low-resolution pixels.
@@ -257,9 +247,17 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     const float wy1 = (iy1 >= 0 && iy1 < h) ? deconv_w(y - 8 * iy1 + 4, 16) : 0.f;
     const float2* r0 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy0, 0), h - 1)) * w * No);
     const float2* r1 = reinterpret_cast<const float2*>(lr + ((size_t)n * h + min(max(iy1, 0), h - 1)) * w * No);
-    for (int i = s_lo * N2 + t; i < s_hi * N2; i += 256) {
-        const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
-        rowi[i] = make_float2(fmaf(wy1, b.x, wy0 * a.x), fmaf(wy1, b.y, wy0 * a.y));
+    if (vertex) {
+        for (int i = s_lo * N2 + t; i < s_hi * N2; i += 256) {
+            const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
+            rowi[i] = make_float2(up8_vblend(wy0, a.x, wy1, b.x), up8_vblend(wy0, a.y, wy1, b.y));
+        }
+    } else {   // label-only mode (the pipeline's Hough samples its vertex values from `lowres` itself): score channels only
+        for (int j = t; j < (s_hi - s_lo) * C2; j += 256) {
+            const int i = (s_lo + j / C2) * N2 + j % C2;
+            const float2 a = __ldg(r0 + i), b = __ldg(r1 + i);
+            rowi[i] = make_float2(up8_vblend(wy0, a.x, wy1, b.x), up8_vblend(wy0, a.y, wy1, b.y));
+        }
     }
     __syncthreads();
     const size_t rowbase = ((size_t)n * H + y) * W;
@@ -268,10 +266,11 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
 #define PCNN_UP8_BLEND(tx, v0, v1)                                                                             \
     const float wa = deconv_w(tx < 4 ? tx + 12 : tx + 4, 16), wb = deconv_w(tx < 4 ? tx + 4 : tx - 4, 16);     \
     const float2 a = tx < 4 ? vl : vc, b = tx < 4 ? vc : vr;                                                   \
-    float v0 = fmaf(wb, b.x, wa * a.x) + bb.x;                                                                 \
-    float v1 = fmaf(wb, b.y, wa * a.y) + bb.y;
-    const int gv = 256 / N2;                 // cell phases; vertex threads [0, gv*V2), score threads [gv*V2, gv*N2)
-    const int nv = gv * V2;
+    float v0 = up8_hblend(wa, a.x, wb, b.x, bb.x);                                                             \
+    float v1 = up8_hblend(wa, a.y, wb, b.y, bb.y);
+    // cell phases; vertex threads [0, gv*V2), score threads [gv*V2, gv*N2); label-only mode: all threads on scores
+    const int gv = vertex ? 256 / N2 : min(256 / C2, seg_cells);
+    const int nv = vertex ? gv * V2 : 0;
     if (t < nv) {
         const int g = t / V2, c2 = t - g * V2;                   // vertex channel pair c2 (channels C + 2 c2, +1 of a lowres cell)
         const float2 bb = make_float2(bias_v[2 * c2], bias_v[2 * c2 + 1]);
@@ -288,7 +287,7 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
                 __stcs(reinterpret_cast<float2*>(vp + tx * 3 * C), make_float2(v0, v1));
             }
         }
-    } else if (t < gv * N2) {
+    } else if (t < nv + gv * C2) {
         const int u = t - nv;
         const int g = u / C2, c2 = u - g * C2;                   // score channel pair
         const float2 bb = make_float2(bias_s[2 * c2], bias_s[2 * c2 + 1]);
@@ -398,7 +397,8 @@ extern "C" int pcnn_lowres_heads(const void* score4, const void* score5, const v
 extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, const float* bias_vertex, int B, int h, int w, int C,
                               int32_t* label, float* vertex, float* prob, float* score, void* stream)
 {
-    PCNN_REQUIRE(lowres && bias_score && bias_vertex && label && vertex, "up8_heads: NULL tensor pointer");
+    // vertex == NULL: label-only mode (label_2d / prob / score; the dense vertex_pred is not produced)
+    PCNN_REQUIRE(lowres && bias_score && label && (bias_vertex || !vertex), "up8_heads: NULL tensor pointer");
     PCNN_REQUIRE(C >= 1 && B >= 1 && h >= 1 && w >= 1, "up8_heads: bad shape");
     PCNN_REQUIRE(8 * h <= 65535 * 1 && B <= 65535, "up8_heads: image too tall for the launch grid");
     PCNN_REQUIRE(C % 2 == 0 && 2 * C <= 256, "up8_heads: num_classes must be even and <= 128 (got %d)", C);

@@ -34,6 +34,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "heads_common.cuh"
 
 namespace pcnn {
 namespace hough {
@@ -53,6 +54,18 @@ struct __align__(16) Sample {
     float d;      // exp(vertex channel 3c+2)
 };
 static_assert(sizeof(Sample) == 32, "sample record is two 16-byte vectors");
+
+// Where k_emit gets a sampled pixel's (u, v, log z): the dense vertex_pred tensor [B,H,W,3C] (the op's registered
+// input, hough_voting_gpu_op.cc:37-52), or — inside the network pipeline — the 1/8-resolution head tensor
+// `lowres` [B,H/8,W/8,4C] (channels C.. = vertex head before the x8 bilinear up-sampling) + the vertex_pred bias:
+// the three values are then computed on demand with k_up8_heads' own operation sequence (heads_common.cuh), so the
+// 2.6 GB dense tensor (batch 32) is never written.  Bit-identical results (tests/test_network_gpu.py).
+struct VertexSrc {
+    const float* dense;
+    const float* lowres;
+    const float* bias;
+    int h, w;   // low-resolution size (H / 8, W / 8)
+};
 
 struct Layout {
     int nchunks, nbands, R, samp_cap, cand_cap;
@@ -208,7 +221,7 @@ k_hist(const int* __restrict__ label, int HW, int C, int nchunks, int* __restric
 // canonical list order of SURVEY.md §8(c))
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const float* __restrict__ extents,
+k_emit(const int* __restrict__ label, const VertexSrc vsrc, const float* __restrict__ extents,
        const float* __restrict__ meta_all, int H, int W, int C, int num_meta, int nchunks, int skip, int label_thr,
        float inlier, const int* __restrict__ chunk_hist, const int* __restrict__ cls_size, int* __restrict__ cls_slot,
        int* __restrict__ cls_nsamp, int* __restrict__ cls_soff, int* __restrict__ slot_cls, int* __restrict__ img_count,
@@ -327,8 +340,16 @@ k_emit(const int* __restrict__ label, const float* __restrict__ vertex, const fl
         const int p = chunk * kChunk + (qe.x & 0xffff);
         {
             int x = p % W, y = p / W;
-            size_t off = (size_t)3 * cls + (size_t)3 * C * ((size_t)b * HW + p);
-            float u = vertex[off], v = vertex[off + 1], z = vertex[off + 2];
+            float u, v, z;
+            if (vsrc.dense) {
+                size_t off = (size_t)3 * cls + (size_t)3 * C * ((size_t)b * HW + p);
+                u = vsrc.dense[off]; v = vsrc.dense[off + 1]; z = vsrc.dense[off + 2];
+            } else {
+                const int ch = C + 3 * cls;   // lowres channel of vertex_pred channel 3 cls
+                u = up8_value(vsrc.lowres, b, vsrc.h, vsrc.w, 4 * C, ch, y, x, __ldg(vsrc.bias + 3 * cls));
+                v = up8_value(vsrc.lowres, b, vsrc.h, vsrc.w, 4 * C, ch + 1, y, x, __ldg(vsrc.bias + 3 * cls + 1));
+                z = up8_value(vsrc.lowres, b, vsrc.h, vsrc.w, 4 * C, ch + 2, y, x, __ldg(vsrc.bias + 3 * cls + 2));
+            }
             float d = expf(z);
             float n1 = __fsqrt_rn(__fmaf_rn(u, u, __fmul_rn(v, v)));
             float thr = project_box(cls, extents, meta, d, 0.6f);
@@ -833,7 +854,7 @@ __device__ float box_overlap(int cls, const float* __restrict__ extents, const f
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_finalize(int B, int H, int W, int C, int num_meta, int num_gt, int is_train, int cap, int cand_cap, int threshold_mode,
+k_finalize(int B, int batch_offset, int H, int W, int C, int num_meta, int num_gt, int is_train, int cap, int cand_cap, int threshold_mode,
            float per_thr, const float* __restrict__ extents, const float* __restrict__ meta_all,
            const float* __restrict__ gt, const int* __restrict__ slot_cls, const int* __restrict__ cand_key,
            const int* __restrict__ cand_val, const int* __restrict__ cand_n, const float4* __restrict__ cand_data,
@@ -906,7 +927,7 @@ k_finalize(int B, int H, int W, int C, int num_meta, int num_gt, int is_train, i
         float* b0 = top_box + (size_t)roi * 7;
         // `x - bb_width * (0.5 + scale)` is double arithmetic in the reference (.cu.cc:417-420)
         const double f = 0.5 + (double)scale;
-        b0[0] = (float)b;
+        b0[0] = (float)(b + batch_offset);   // global batch index (image shard of a larger batch)
         b0[1] = (float)cls;
         b0[2] = (float)((double)x - (double)bb_width * f);
         b0[3] = (float)((double)y - (double)bb_height * f);
@@ -922,7 +943,7 @@ k_finalize(int B, int H, int W, int C, int num_meta, int num_gt, int is_train, i
         if (!is_train) continue;
         for (int g = 0; g < num_gt; g++) {
             const float* gp = gt + (size_t)g * 13;
-            if (cls == (int)gp[1] && b == (int)gp[0]) {
+            if (cls == (int)gp[1] && b + batch_offset == (int)gp[0]) {
                 if (box_overlap(cls, extents, meta, gp, b0 + 2) > 0.2f) {
                     for (int j = 0; j < 9; j++)
                         for (int k = 0; k < 4; k++) {
@@ -941,7 +962,7 @@ k_finalize(int B, int H, int W, int C, int num_meta, int num_gt, int is_train, i
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             float* q = top_box + (size_t)(roi + 1 + j) * 7;
-            q[0] = (float)b;
+            q[0] = (float)(b + batch_offset);
             q[1] = (float)cls;
             q[2] = jx[j] == 0 ? x1 : (float)((double)x1 + jx[j] * (0.05 * (double)ww));
             q[3] = jy[j] == 0 ? y1 : (float)((double)y1 + jy[j] * (0.05 * (double)hh));
@@ -962,7 +983,7 @@ __global__ void k_zero2(float* a, size_t na, float* b, size_t nb)
 }
 
 // host side --------------------------------------------------------------------------------
-static int run_front(const Layout& L, char* ws, const int32_t* label, const float* vertex, const float* extents,
+static int run_front(const Layout& L, char* ws, const int32_t* label, const VertexSrc vertex, const float* extents,
                      const float* meta, int B, int H, int W, int C, int num_meta, float inlier, int label_thr, int skip,
                      ZeroList z, float* votes_out, cudaStream_t st)
 {
@@ -1024,20 +1045,23 @@ extern "C" int pcnn_hough_vote_workspace_bytes(int B, int H, int W, int C, int s
     return PCNN_OK;
 }
 
-extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, const float* extents, const float* meta,
-                                   const float* gt, int B, int H, int W, int C, int num_gt, int num_meta, int is_train,
-                                   float inlier_threshold, int label_threshold, float threshold_vote,
-                                   float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
-                                   float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
-                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream)
+static int hough_fwd_impl(const int32_t* label, const VertexSrc vsrc, const float* extents, const float* meta,
+                          const float* gt, int B, int batch_global, int batch_offset, int H, int W, int C, int num_gt,
+                          int num_meta, int is_train, float inlier_threshold, int label_threshold, float threshold_vote,
+                          float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
+                          float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
+                          int32_t* status, void* workspace, size_t workspace_bytes, void* stream)
 {
     int rc = validate(B, H, W, C, skip_pixels);
     if (rc) return rc;
     PCNN_REQUIRE(is_train >= 0, "Need is_train >= 0, got %d", is_train);  // hough_voting_gpu_op.cc:309-311
     PCNN_REQUIRE(num_meta >= 6, "hough: meta_data needs the intrinsics (num_meta >= 6, got %d)", num_meta);
     PCNN_REQUIRE(num_gt == 0 || gt != nullptr, "hough: gt is NULL but num_gt = %d", num_gt);
-    PCNN_REQUIRE(label && vertex && extents && meta && top_box && top_pose && top_target && top_weight && top_domain &&
-                     num_rois && workspace, "hough: NULL tensor pointer");
+    PCNN_REQUIRE(label && (vsrc.dense || (vsrc.lowres && vsrc.bias)) && extents && meta && top_box && top_pose &&
+                     top_target && top_weight && top_domain && num_rois && workspace, "hough: NULL tensor pointer");
+    PCNN_REQUIRE(batch_global >= B && batch_offset >= 0 && batch_offset + B <= batch_global,
+                 "hough: shard [%d, %d) does not lie inside the global batch of %d images", batch_offset, batch_offset + B,
+                 batch_global);
     const bool thr_mode = threshold_vote > 0;
     size_t need = 0;
     pcnn_hough_vote_workspace_bytes(B, H, W, C, skip_pixels, threshold_vote, &need);
@@ -1059,7 +1083,7 @@ extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, co
     z.p[4] = reinterpret_cast<float*>(top_domain); z.n[4] = rows;
     if (status) cudaMemsetAsync(status, 0, 4 * sizeof(int), st);
     float* votes = thr_mode ? (float*)(ws + L.votes) : nullptr;
-    rc = run_front(L, ws, label, vertex, extents, meta, B, H, W, C, num_meta, inlier_threshold, label_threshold,
+    rc = run_front(L, ws, label, vsrc, extents, meta, B, H, W, C, num_meta, inlier_threshold, label_threshold,
                    skip_pixels, z, votes, st);
     if (rc) return rc;
     int* img_count = (int*)(ws + L.img_count);
@@ -1069,7 +1093,9 @@ extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, co
     int* cand_val = (int*)(ws + L.cand_val);
     int* cand_n = (int*)(ws + L.cand_n);
     float4* cand_data = (float4*)(ws + L.cand_data);
-    const int cap = PCNN_MAX_ROI / B;  // .cu.cc:733
+    // .cu.cc:733: index_size = MAX_ROI / batch_size — of the WHOLE batch the reference op would see; a rank that
+    // holds images [batch_offset, batch_offset + B) of it applies the same cap
+    const int cap = PCNN_MAX_ROI / batch_global;
     if (!thr_mode) {
         k_select<<<B, 32, 0, st>>>(C, H * W, L.R, L.nbands, cap, L.cand_cap, img_count, slot_cls, bbox,
                                    (const int2*)(ws + L.band_res), cand_key, cand_val, cand_n);
@@ -1082,11 +1108,40 @@ extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, co
     k_celldata<<<gcell, kThreads, 0, st>>>(B, H, W, C, num_meta, inlier_threshold, L.cand_cap, extents, meta, slot_cls,
                                              (const int*)(ws + L.cls_nsamp), (const int*)(ws + L.cls_soff),
                                              (const Sample*)(ws + L.samples), L.samp_cap, cand_key, cand_n, cand_data);
-    k_finalize<<<1, kThreads, 0, st>>>(B, H, W, C, num_meta, num_gt, is_train, cap, L.cand_cap, thr_mode ? 1 : 0,
-                                       threshold_percentage, extents, meta, gt, slot_cls, cand_key, cand_val, cand_n,
-                                       cand_data, sel, sel_n, top_box, top_pose, top_target, top_weight, top_domain,
+    k_finalize<<<1, kThreads, 0, st>>>(B, batch_offset, H, W, C, num_meta, num_gt, is_train, cap, L.cand_cap,
+                                       thr_mode ? 1 : 0, threshold_percentage, extents, meta, gt, slot_cls, cand_key, cand_val,
+                                       cand_n, cand_data, sel, sel_n, top_box, top_pose, top_target, top_weight, top_domain,
                                        num_rois, status);
     return check_launch("hough back kernels");
+}
+
+extern "C" int pcnn_hough_vote_fwd(const int32_t* label, const float* vertex, const float* extents, const float* meta,
+                                   const float* gt, int B, int H, int W, int C, int num_gt, int num_meta, int is_train,
+                                   float inlier_threshold, int label_threshold, float threshold_vote,
+                                   float threshold_percentage, int skip_pixels, float* top_box, float* top_pose,
+                                   float* top_target, float* top_weight, int32_t* top_domain, int32_t* num_rois,
+                                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream)
+{
+    VertexSrc vs = {vertex, nullptr, nullptr, 0, 0};
+    return hough_fwd_impl(label, vs, extents, meta, gt, B, B, 0, H, W, C, num_gt, num_meta, is_train, inlier_threshold,
+                          label_threshold, threshold_vote, threshold_percentage, skip_pixels, top_box, top_pose, top_target,
+                          top_weight, top_domain, num_rois, status, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pcnn_hough_vote_fwd_ex(const int32_t* label, const float* vertex, const float* lowres,
+                                      const float* bias_vertex, const float* extents, const float* meta, const float* gt,
+                                      int B, int batch_global, int batch_offset, int H, int W, int C, int num_gt,
+                                      int num_meta, int is_train, float inlier_threshold, int label_threshold,
+                                      float threshold_vote, float threshold_percentage, int skip_pixels, float* top_box,
+                                      float* top_pose, float* top_target, float* top_weight, int32_t* top_domain,
+                                      int32_t* num_rois, int32_t* status, void* workspace, size_t workspace_bytes,
+                                      void* stream)
+{
+    PCNN_REQUIRE(vertex || (H % 8 == 0 && W % 8 == 0), "hough: the lowres vertex source needs H, W multiples of 8 (got %d x %d)", H, W);
+    VertexSrc vs = {vertex, vertex ? nullptr : lowres, vertex ? nullptr : bias_vertex, H / 8, W / 8};
+    return hough_fwd_impl(label, vs, extents, meta, gt, B, batch_global, batch_offset, H, W, C, num_gt, num_meta, is_train,
+                          inlier_threshold, label_threshold, threshold_vote, threshold_percentage, skip_pixels, top_box,
+                          top_pose, top_target, top_weight, top_domain, num_rois, status, workspace, workspace_bytes, stream);
 }
 
 extern "C" int pcnn_hough_vote_planes(const int32_t* label, const float* vertex, const float* extents, const float* meta,
@@ -1106,7 +1161,8 @@ extern "C" int pcnn_hough_vote_planes(const int32_t* label, const float* vertex,
     cudaMemsetAsync(votes, 0, sizeof(float) * (size_t)B * C * H * W, st);
     ZeroList z;
     for (int k = 0; k < 5; k++) { z.p[k] = nullptr; z.n[k] = 0; }
-    return run_front(L, (char*)workspace, label, vertex, extents, meta, B, H, W, C, num_meta, inlier_threshold,
+    VertexSrc vs = {vertex, nullptr, nullptr, 0, 0};
+    return run_front(L, (char*)workspace, label, vs, extents, meta, B, H, W, C, num_meta, inlier_threshold,
                      label_threshold, skip_pixels, z, votes, st);
 }
 

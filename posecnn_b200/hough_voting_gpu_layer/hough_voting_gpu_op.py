@@ -24,17 +24,33 @@ LABEL_THRESHOLD = 500       # hough_voting_gpu_op.cc:357
 
 def hough_voting_gpu_capacity(bottom_label, bottom_vertex, bottom_extents, bottom_meta_data, bottom_gt, is_train,
                               threshold_vote, threshold_percentage, skip_pixels,
-                              inlier_threshold=INLIER_THRESHOLD, label_threshold=LABEL_THRESHOLD):
+                              inlier_threshold=INLIER_THRESHOLD, label_threshold=LABEL_THRESHOLD,
+                              lowres=None, bias_vertex=None, batch_global=None, batch_offset=0):
     """Stream-ordered form: returns the five 1152-row capacity buffers, the device row
-    count [1] int32 and a device status word; no host synchronisation."""
+    count [1] int32 and a device status word; no host synchronisation.
+
+    Pipeline extensions (pcnn_hough_vote_fwd_ex): `bottom_vertex=None` + `lowres` [B,H/8,W/8,4C] + `bias_vertex` [3C]
+    samples the vertex head on demand instead of reading a dense vertex_pred (bit-identical); `batch_global` /
+    `batch_offset` make this call one image shard of a larger batch (ROI cap 128 // batch_global, global batch indices)."""
     label = require_cuda("bottom_label", bottom_label, torch.int32, 3)       # .cc:328-329
-    vertex = require_cuda("bottom_vertex", bottom_vertex, torch.float32, 4)  # .cc:331-332
     extents = require_cuda("bottom_extents", bottom_extents, torch.float32)
     meta = require_cuda("bottom_meta_data", bottom_meta_data, torch.float32)
     B, H, W = label.shape
-    if vertex.shape[0] != B or vertex.shape[1] != H or vertex.shape[2] != W or vertex.shape[3] % 3:
-        raise ValueError("bottom_vertex must be [B,H,W,3*num_classes] matching bottom_label")
-    C = vertex.shape[3] // 3
+    if bottom_vertex is not None:
+        vertex = require_cuda("bottom_vertex", bottom_vertex, torch.float32, 4)  # .cc:331-332
+        if vertex.shape[0] != B or vertex.shape[1] != H or vertex.shape[2] != W or vertex.shape[3] % 3:
+            raise ValueError("bottom_vertex must be [B,H,W,3*num_classes] matching bottom_label")
+        C = vertex.shape[3] // 3
+        lowres = bias_vertex = None
+    else:
+        vertex = None
+        lowres = require_cuda("lowres", lowres, torch.float32, 4)
+        bias_vertex = require_cuda("bias_vertex", bias_vertex, torch.float32, 1)
+        if lowres.shape[0] != B or lowres.shape[1] * 8 != H or lowres.shape[2] * 8 != W or lowres.shape[3] % 4:
+            raise ValueError("lowres must be [B,H/8,W/8,4*num_classes] matching bottom_label")
+        C = lowres.shape[3] // 4
+        if bias_vertex.numel() != 3 * C:
+            raise ValueError("bias_vertex must be [3*num_classes]")
     if extents.numel() != C * 3:
         raise ValueError("bottom_extents must be [num_classes,3]")
     num_meta = meta.shape[-1]
@@ -45,6 +61,7 @@ def hough_voting_gpu_capacity(bottom_label, bottom_vertex, bottom_extents, botto
     else:
         gt = require_cuda("bottom_gt", bottom_gt, torch.float32).reshape(-1, 13)
         num_gt = gt.shape[0]
+    bg = B if batch_global is None else int(batch_global)
     dev = label.device
     box = torch.empty((MAX_ROWS, 7), dtype=torch.float32, device=dev)
     pose = torch.empty((MAX_ROWS, 7), dtype=torch.float32, device=dev)
@@ -56,8 +73,9 @@ def hough_voting_gpu_capacity(bottom_label, bottom_vertex, bottom_extents, botto
     nbytes = ctypes.c_size_t(0)
     check(lib().pcnn_hough_vote_workspace_bytes(B, H, W, C, int(skip_pixels), f32(threshold_vote), ctypes.byref(nbytes)))
     ws = workspace("hough", nbytes.value, dev)
-    check(lib().pcnn_hough_vote_fwd(
-        ptr(label), ptr(vertex), ptr(extents), ptr(meta), ptr(gt), B, H, W, C, num_gt, num_meta, int(is_train),
+    check(lib().pcnn_hough_vote_fwd_ex(
+        ptr(label), ptr(vertex), ptr(lowres), ptr(bias_vertex), ptr(extents), ptr(meta), ptr(gt), B, bg, int(batch_offset),
+        H, W, C, num_gt, num_meta, int(is_train),
         f32(inlier_threshold), int(label_threshold), f32(threshold_vote), f32(threshold_percentage), int(skip_pixels),
         ptr(box), ptr(pose), ptr(target), ptr(weight), ptr(domain), ptr(num_rois), ptr(status), ptr(ws),
         ctypes.c_size_t(ws.numel()), stream()))

@@ -8,9 +8,9 @@ vgg16_convs.setup() (vgg16_convs.py:79-212) is executed eagerly on one CUDA stre
     conv1_1 .. conv5_3 (+ _p trunk for RGBD)   tcgen05 implicit GEMM, bf16 x bf16 -> fp32   csrc/conv_tc.cu
     score / vertex heads                         1x1 on tcgen05 + fused bilinear/softmax     csrc/heads.cu
     hough_voting_gpu                             csrc/hough_vote.cu
-    roi_pool x2, add, fc6-fc8, tanh              csrc/pixel_ops.cu + cuBLAS (plain library GEMMs)
+    roi_pool x2 + add, fc6-fc8, tanh             csrc/fc_tc.cu (fused pooling, split-K tcgen05 GEMMs, fused epilogues)
 
-PyTorch supplies device memory, streams and the three fully connected GEMMs only.
+PyTorch supplies device memory and streams only.
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import math
 import numpy as np
 import torch
 
-from .. import conv
+from .. import conv, pose_head
 from .._lib import check, lib, ptr, stream
 from ..hough_voting_gpu_layer import hough_voting_gpu_op
 from ..roi_pooling_layer import roi_pooling_op
@@ -95,11 +95,11 @@ class vgg16_convs:
         self.prepare()
         return self
 
-    def calibrate_background(self, data, meta_data, extents, background_fraction=0.75):
+    def calibrate_background(self, data, meta_data, extents, background_fraction=0.75, **forward_kwargs):
         """Benchmark-harness helper: a randomly initialised net labels (almost) every pixel as foreground, which is
         not what the Hough layer sees in use.  Shift `score/biases[0]` so that about `background_fraction` of the
         pixels of this batch are labelled background (YCB-like fill).  Declared in bench.py's config."""
-        self.forward(data, meta_data, extents, want_prob=False, sync_rois=False)
+        self.forward(data, meta_data, extents, want_prob=False, sync_rois=False, **forward_kwargs)
         C = self.num_classes
         B, H, W, _ = data.shape
         lab = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
@@ -152,8 +152,7 @@ class vgg16_convs:
             else:
                 T[name] = conv.hwio_to_tc(w)
         for name in ("fc6", "fc7", "fc8"):
-            T[f"{name}/weights"] = P[f"{name}/weights"].t().contiguous().to(torch.bfloat16)  # [out, in] for F.linear
-            T[f"{name}/biases"] = P[f"{name}/biases"].to(torch.bfloat16)
+            T[f"{name}/weights"] = pose_head.fc_weights_to_tc(P[f"{name}/weights"])   # [out (padded to x128), in] bf16
         T["score/w"] = P["score/weights"].reshape(self.num_units, self.num_classes).contiguous()
         T["vertex_pred/w"] = P["vertex_pred/weights"].reshape(128, 3 * self.num_classes).contiguous()
         if self.fold_vertex_head:
@@ -170,10 +169,14 @@ class vgg16_convs:
     # ------------------------------------------------------------------ graph pieces
     def _trunk(self, data, sfx=""):
         """13 x (conv3x3 + bias + ReLU), 4 x max-pool (vgg16_convs.py:80-97).  data: [B,H,W,3] u8 (BGR, mean
-        subtracted on the fly) or f32 (already pre-processed)."""
+        subtracted on the fly) or f32 (already pre-processed), or [B,H,W] f32 = a RAW depth image (sensor units) whose
+        blob clip(d / 2000, 0, 1) * 255 x3 - PIXEL_MEANS (lib/fcn/test.py:70-76) is formed in the conv1_1 loader."""
         P, T = self.params, self._tc
-        mean = PIXEL_MEANS if data.dtype == torch.uint8 else None
-        x = conv.conv1_fused(data, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], mean, True)
+        if data.dim() == 3:
+            x = conv.conv1_depth_fused(data, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], PIXEL_MEANS, True)
+        else:
+            mean = PIXEL_MEANS if data.dtype == torch.uint8 else None
+            x = conv.conv1_fused(data, T[f"conv1_1{sfx}/weights"], P[f"conv1_1{sfx}/biases"], mean, True)
         feats = {}
         cfg = VGG_CFG[1:]
         i = 0
@@ -195,9 +198,16 @@ class vgg16_convs:
             i += 1
         return feats
 
-    def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True, want_score=False):
+    def forward(self, data, meta_data, extents, poses=None, data_p=None, want_prob=False, sync_rois=True, want_score=False,
+                dense_vertex=True, batch_global=None, batch_offset=0, depth=None):
         """Inference / forward pass.  data [B,H,W,3] (u8 BGR or pre-processed f32), H, W multiples of 16
-        (pad_im, lib/utils/blob.py:48-58).  Returns self.layers with the reference's layer names."""
+        (pad_im, lib/utils/blob.py:48-58).  Returns self.layers with the reference's layer names.
+
+        dense_vertex=False: the pipeline mode — `vertex_pred` [B,H,W,3C] (81 MB / frame, only read back by the
+        reference for visualisation, lib/fcn/test.py:587-599) is not materialised; Houghvotinggpu samples the vertex
+        head on demand from the 1/8-resolution head tensor (bit-identical ROIs, pcnn_hough_vote_fwd_ex).
+        batch_global / batch_offset: this call is the image shard [batch_offset, batch_offset + B) of a batch of
+        batch_global images (SURVEY.md §8(e)): ROI budget 128 // batch_global per image, global batch indices."""
         C = self.num_classes
         L = self.layers = {}
         P, T = self.params, self._tc
@@ -207,7 +217,8 @@ class vgg16_convs:
         c4, c5 = f["conv4_3"], f["conv5_3"]
         L["conv4_3"], L["conv5_3"] = c4, c5
         if self.input_format == "RGBD":
-            fp = self._trunk(data_p, "_p")
+            # data_p: the pre-processed depth blob [B,H,W,3] f32, or depth= the raw depth image [B,H,W] f32 (fused blob)
+            fp = self._trunk(depth if depth is not None else data_p, "_p")
             h4, h5 = torch.cat([c4, fp["conv4_3"]], 3), torch.cat([c5, fp["conv5_3"]], 3)  # concat_conv4/5
         else:
             h4, h5 = c4, c5
@@ -230,34 +241,46 @@ class vgg16_convs:
                                       self.num_units, 128, C, ptr(lowres), stream()))
         self._last_lowres = lowres
         label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
-        vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
+        vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device) if dense_vertex else None
         prob = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_prob else None
         score = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device) if want_score else None
         check(lib().pcnn_up8_heads(ptr(lowres), ptr(P["score/biases"]), ptr(P["vertex_pred/biases"]), B, h, w, C, ptr(label),
                                    ptr(vertex), ptr(prob), ptr(score), stream()))
-        L["label_2d"], L["vertex_pred"] = label, vertex
+        L["label_2d"] = label
+        if dense_vertex:
+            L["vertex_pred"] = vertex
         if want_prob:
             L["prob_normalized"] = prob
         if want_score:
             L["score"] = score
         if not self.vertex_reg_2d:
             return L
+        Bg = B if batch_global is None else int(batch_global)
         box, pose, target, weight, domain, num_rois, status = hough_voting_gpu_op.hough_voting_gpu_capacity(
-            label, vertex, extents, meta_data, poses, self.is_train, self.vote_threshold, self.vote_percentage, self.skip_pixels)
-        # fixed-shape pose head over the ROI capacity of this batch size (rows beyond num_rois are all-zero ROIs)
-        cap_rows = max(1, min(box.shape[0], (128 // B) * B * (9 if self.is_train else 1)))
+            label, vertex, extents, meta_data, poses, self.is_train, self.vote_threshold, self.vote_percentage, self.skip_pixels,
+            lowres=lowres, bias_vertex=P["vertex_pred/biases"], batch_global=Bg, batch_offset=batch_offset)
+        # fixed-shape pose head over the ROI capacity of this shard (rows beyond num_rois are all-zero ROIs)
+        cap_rows = max(1, min(box.shape[0], (128 // Bg) * B * (9 if self.is_train else 1)))
         rois = box[:cap_rows]
         L["rois_capacity"], L["num_rois"] = rois, num_rois
         L["hough_status"] = status      # device status word (overflow bit, scan/recount mismatches); read in the sync path
         L["poses_init"], L["poses_target"], L["poses_weight"] = pose[:cap_rows], target[:cap_rows], weight[:cap_rows]
         if self.pose_reg:
-            p5, _ = roi_pooling_op.roi_pool(c5, rois, 7, 7, 1.0 / 16.0, 0)
-            p4, _ = roi_pooling_op.roi_pool(c4, rois, 7, 7, 1.0 / 8.0, 0)
-            x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                     # pool_score, flatten (h, w, c)
-            x = torch.relu(torch.nn.functional.linear(x, T["fc6/weights"], T["fc6/biases"]))
-            x = torch.relu(torch.nn.functional.linear(x, T["fc7/weights"], T["fc7/biases"]))
-            x = torch.nn.functional.linear(x, T["fc8/weights"], T["fc8/biases"]).float()
-            L["poses_tanh"] = torch.tanh(x)
+            if self.is_train:
+                # training graph: the reference ops with arg-max outputs for RoiPoolGrad (roi_pooling_op_grad.py:29-50)
+                rl = rois if not batch_offset else torch.cat([rois[:, :1] - float(batch_offset), rois[:, 1:]], 1)
+                p5, a5 = roi_pooling_op.roi_pool(c5, rl, 7, 7, 1.0 / 16.0, 0)
+                p4, a4 = roi_pooling_op.roi_pool(c4, rl, 7, 7, 1.0 / 8.0, 0)
+                L["pool5_argmax"], L["pool4_argmax"] = a5, a4
+                x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                 # pool_score, flatten (h, w, c)
+            else:
+                x = pose_head.roi_pool_pair(c5, c4, rois, 7, 7, 1.0 / 16.0, 1.0 / 8.0, batch_offset)
+            L["pool_score"] = x
+            x = pose_head.fc(x, T["fc6/weights"], P["fc6/biases"], "relu")             # fc6 + ReLU (dropout keep_prob = 1)
+            L["fc6"] = x
+            x = pose_head.fc(x, T["fc7/weights"], P["fc7/biases"], "relu")
+            L["fc7"] = x
+            L["poses_tanh"] = pose_head.fc(x, T["fc8/weights"], P["fc8/biases"], "tanh", torch.float32)   # fc8 + tanh
         if not self.is_train:
             # test-time post-processing on the device: per-class NMS + pose assembly (lib/utils/nms.py, test.py:197-211)
             keep, d_rois, d_poses, d_n = dev_nms.nms_pose_capacity(rois, L["poses_init"], L.get("poses_tanh"), num_rois,
@@ -321,8 +344,20 @@ class GraphedForward:
     """The whole forward pass captured once into a CUDA graph (all shapes are static: Hough outputs are capacity
     buffers + a device row count).  Replays remove the ~60 per-launch host calls of the eager path."""
 
-    def __init__(self, net: vgg16_convs, data: torch.Tensor, meta_data: torch.Tensor, extents: torch.Tensor, warmup: int = 2):
+    def __init__(self, net: vgg16_convs, data: torch.Tensor, meta_data: torch.Tensor, extents: torch.Tensor, warmup: int = 2,
+                 pack_records: bool = False, **forward_kwargs):
+        """pack_records: also capture parallel.pack_detections (the fixed-size post-NMS records a rank all-gathers)
+        into the graph -> self.layers["records"]; forward_kwargs go to net.forward (dense_vertex, batch_global, ...)."""
         self.net = net
+        kw = dict(sync_rois=False)
+        kw.update(forward_kwargs)
+
+        def run():
+            L = dict(net.forward(self.s_data, self.s_meta, self.s_ext, **kw))
+            if pack_records:
+                from .. import parallel
+                L["records"] = parallel.pack_detections(L)
+            return L
         self.s_data = data.clone()
         self.s_meta = meta_data.clone()
         self.s_ext = extents.clone()
@@ -330,12 +365,12 @@ class GraphedForward:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                net.forward(self.s_data, self.s_meta, self.s_ext, sync_rois=False)
+                run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.layers = dict(net.forward(self.s_data, self.s_meta, self.s_ext, sync_rois=False))
+            self.layers = run()
 
     def __call__(self, data: torch.Tensor, meta_data: torch.Tensor | None = None):
         self.s_data.copy_(data, non_blocking=True)

@@ -30,15 +30,23 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     C, cap, local_batch = 6, 16, 4
     L = _fake_layers(rank, C, cap, n_valid=5 + 3 * rank)
-    rec = parallel.pack_records(L, C, rank, local_batch)
+    rec = parallel.pack_records(L, C, rank * local_batch)
     allrec = parallel.all_gather_records(rec, world)
     # post-NMS detections (final payload) and the training-side loss normaliser
     nd = 2 + rank
     L.update(detections_rois=L["rois_capacity"].clone(), detections_poses=L["poses_init"].clone(),
              num_detections=torch.tensor([nd], dtype=torch.int32))
-    det = parallel.all_gather_records(parallel.pack_detections(L, rank, local_batch), world)
+    det = parallel.all_gather_records(parallel.pack_detections(L, rank * local_batch), world)
+    # the per-step pipeline (double-buffered copy + collective; CPU tensors take the stream-less branch of the same protocol)
+    pipe = parallel.GatherPipeline(world, rec)
+    piped = []
+    for step in range(3):
+        pipe.before_step()
+        i = pipe.submit(rec + float(step))
+        piped.append(pipe.results(i).clone())
+    pipe.drain()
     loss, gscale = parallel.global_mean_loss(torch.tensor(1.0 + rank), 3 + 5 * rank, world)
-    torch.save(dict(rec=rec, allrec=allrec, det=det, loss=loss, gscale=gscale), os.path.join(out_dir, f"r{rank}.pt"))
+    torch.save(dict(rec=rec, allrec=allrec, det=det, loss=loss, gscale=gscale, piped=piped), os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,6 +74,9 @@ def test_all_gather_records_gloo_world2(tmp_path):
         assert torch.equal(det[:2 + r, 7:14], L["poses_init"][:2 + r])
         np.testing.assert_array_equal(det[:2 + r, 0].numpy(), (L["rois_capacity"][:2 + r, 0] + r * local_batch).numpy())
     assert torch.equal(outs[0]["det"], outs[1]["det"])
+    for step in range(3):   # GatherPipeline: every rank sees [rank 0 records | rank 1 records] of that step
+        want = torch.cat([outs[0]["rec"] + float(step), outs[1]["rec"] + float(step)])
+        assert torch.equal(outs[0]["piped"][step], want) and torch.equal(outs[1]["piped"][step], want)
     # ranks hold means 1.0 (3 rows) and 2.0 (8 rows): global mean = (3 + 16) / 11; grad scales N_r * world / N
     assert abs(outs[0]["loss"].item() - 19.0 / 11.0) < 1e-6 and abs(outs[1]["loss"].item() - 19.0 / 11.0) < 1e-6
     assert abs(outs[0]["gscale"].item() - 6.0 / 11.0) < 1e-6 and abs(outs[1]["gscale"].item() - 16.0 / 11.0) < 1e-6
@@ -73,7 +84,22 @@ def test_all_gather_records_gloo_world2(tmp_path):
 
 def test_pack_records_single_process():
     L = _fake_layers(0, 4, 8, 3)
-    rec = parallel.pack_records(L, 4, rank=2, local_batch=32)
+    rec = parallel.pack_records(L, 4, batch_offset=64)
     assert rec.shape == (8, parallel.record_width(4))
     assert rec[:3, 0].tolist() == [64.0, 65.0, 66.0] and rec[3:, 0].abs().sum() == 0
     assert parallel.all_gather_records(rec, 1) is rec
+
+
+def test_shard_range_and_capacity():
+    """contiguous shards of ONE global batch; ROI budget from the global batch size."""
+    for B, G in ((32, 1), (32, 2), (32, 4), (32, 8), (10, 4), (3, 8)):
+        parts = [parallel.shard_range(B, r, G) for r in range(G)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == B
+        for (o0, c0), (o1, _) in zip(parts, parts[1:]):
+            assert o1 == o0 + c0
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    assert parallel.roi_capacity(32, 32) == 128 and parallel.roi_capacity(32, 4) == 16    # 128 // 32 = 4 maxima per image
+    assert parallel.roi_capacity(64, 8, is_train=True) == 2 * 8 * 9 and parallel.roi_capacity(256, 32) == 1
+    table = torch.zeros((6, parallel.detection_width()))
+    table[[0, 1, 3], -1] = 1.0
+    assert parallel.compact_records(table).shape[0] == 3
