@@ -262,6 +262,19 @@ int pcnn_nms_pose_fwd(const float* rois, const float* poses_init, const float* p
  * Both losses reduce per-CTA partial sums (double) in index order: run-to-run deterministic.  workspace: zero-filled
  * once by the caller (pcnn_train_loss_workspace_bytes), reusable across launches on one stream.
  */
+/*  pcnn_vertex_targets_instances_fwd   the multi-instance branch of _generate_vertex_targets (minibatch.py:549-573): several
+ *      instances of one class are separated by an instance-mask image; mask [B,H,W] int32, instances [B,I,5] f32 =
+ *      (cls, mask id = cls_indexes_old + 1, cx, cy, z), z <= 0 = unused slot; a pixel with label == cls and mask == id gets
+ *      the target toward that instance's centre (last matching instance wins, like the reference's in-order overwrites).
+ *  pcnn_pack_pose_meta_fwd             the data layer's pose blob and meta_data packing (minibatch.py:440-451, 474-492):
+ *      poses [B,I,12] (3x4 [R|T] row-major per instance), cls [B,I] int32 (< 0 = unused slot), intrinsics [B,9] ->
+ *      pose_blob [B*I,13] rows [image, cls, 0,0,0,0, qw,qx,qy,qz (transforms3d mat2quat, w >= 0), tx,ty,tz] compacted in
+ *      (image, slot) order, rows beyond *num_rows zero; meta [B,48] = K * im_scale (K[2][2] = 1) | its inverse | zeros,
+ *      FLIP_X sign flips of minibatch.py:488-491.  One small launch each; no host synchronisation. */
+int pcnn_vertex_targets_instances_fwd(const int32_t* label, const int32_t* mask, const float* instances, int B, int H, int W,
+                                      int C, int I, float w_inside, float* targets, float* weights, void* stream);
+int pcnn_pack_pose_meta_fwd(const float* poses, const int32_t* cls, const float* intrinsics, int B, int I, float im_scale,
+                            int flip_x, float* pose_blob, int32_t* num_rows, float* meta, void* stream);
 int pcnn_train_loss_workspace_bytes(size_t* bytes);
 int pcnn_vertex_targets_fwd(const int32_t* label, const float* centers, int B, int H, int W, int C, float w_inside,
                             float* targets, float* weights, void* stream);

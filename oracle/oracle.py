@@ -239,6 +239,76 @@ def generate_vertex_targets(label, centers, w_inside):
     return targets, weights
 
 
+def generate_vertex_targets_instances(label, mask, instances, num_classes, w_inside):
+    """lib/gt_synthesize_layer/minibatch.py:549-573 (multi-instance branch, VERTEX_REG_2D): instances [B,I,5] =
+    (cls, mask id = cls_indexes_old + 1, cx, cy, z), z <= 0 = unused slot; in-order overwrites like the reference loop."""
+    label, mask = np.asarray(label), np.asarray(mask)
+    B, H, W = label.shape
+    C = num_classes
+    targets = np.zeros((B, H, W, 3 * C), np.float32)
+    weights = np.zeros((B, H, W, 3 * C), np.float32)
+    for b in range(B):
+        for r in instances[b]:
+            if not r[4] > 0:
+                continue
+            cls = int(r[0])
+            y, x = np.where((mask[b] == int(r[1])) & (label[b] == cls))   # :553
+            if len(x) > 0:
+                c = np.zeros((2, 1), np.float32)
+                c[0], c[1] = r[2], r[3]                                   # :557-558
+                R = np.tile(c, (1, len(x))) - np.vstack((x, y))           # :560
+                N = np.linalg.norm(R, axis=0) + 1e-10
+                R = np.divide(R, np.tile(N, (2, 1)))
+                targets[b, y, x, 3 * cls + 0] = R[0, :]
+                targets[b, y, x, 3 * cls + 1] = R[1, :]
+                targets[b, y, x, 3 * cls + 2] = np.log(np.float64(r[4]))
+                weights[b, y, x, 3 * cls:3 * cls + 3] = w_inside
+    return targets, weights
+
+
+def mat2quat(M):
+    """transforms3d.quaternions.mat2quat (third-party, un-pinned, absent here: `from transforms3d.quaternions import
+    mat2quat`, minibatch.py:18) restated from its published algorithm (Bar-Itzhack 2000): the eigenvector of the largest
+    eigenvalue of the symmetric K matrix, ordered (w, x, y, z), w made non-negative.  Parity unpinned for this function;
+    cross-checked against scipy.spatial.transform.Rotation in tests/test_golden_cpu.py."""
+    Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz = np.asarray(M, np.float64).flat
+    K = np.array([[Qxx - Qyy - Qzz, 0, 0, 0],
+                  [Qyx + Qxy, Qyy - Qxx - Qzz, 0, 0],
+                  [Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, 0],
+                  [Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz]]) / 3.0
+    vals, vecs = np.linalg.eigh(K)
+    q = vecs[[3, 0, 1, 2], np.argmax(vals)]
+    if q[0] < 0:
+        q = -q
+    return q
+
+
+def pack_pose_meta(poses, cls, intrinsics, im_scale=1.0, flip_x=False):
+    """minibatch.py:440-451 (pose blob rows [image, cls, 0,0,0,0, mat2quat(R), T]) and :474-492 (meta_data[48]):
+    poses [B,I,3,4], cls [B,I] (< 0 = unused slot), intrinsics [B,3,3]."""
+    B, I = cls.shape
+    rows = []
+    for b in range(B):
+        for j in range(I):
+            if cls[b, j] < 0:
+                continue
+            qt = np.zeros(13, np.float32)
+            qt[0], qt[1] = b, cls[b, j]
+            qt[6:10] = mat2quat(poses[b, j, :, :3])
+            qt[10:] = poses[b, j, :, 3]
+            rows.append(qt)
+    blob = np.stack(rows) if rows else np.zeros((0, 13), np.float32)
+    meta = np.zeros((B, 48), np.float32)
+    for b in range(B):
+        K = np.asarray(intrinsics[b], np.float32).astype(np.float64) * im_scale
+        K[2, 2] = 1
+        meta[b, 0:9] = K.flatten()
+        meta[b, 9:18] = np.linalg.pinv(K).flatten()
+        if flip_x:
+            meta[b, 0] = -meta[b, 0]; meta[b, 9] = -meta[b, 9]; meta[b, 11] = -meta[b, 11]
+    return blob, meta
+
+
 def loss_cross_entropy_hard(scores, prob, gt, threshold):
     """lib/fcn/train.py:455-465 with labels = Hardlabel(prob, gt, threshold) (network.py:340): float64 accumulation."""
     mask = hard_label(np.asarray(prob, np.float32), np.asarray(gt, np.int32), threshold).astype(np.float64)

@@ -182,6 +182,129 @@ k_vertex_targets_sparse(const int* __restrict__ label, const float* __restrict__
     }
 }
 
+// multi-instance branch of _generate_vertex_targets (minibatch.py:549-573): several instances of one class in an image
+// are told apart by an instance-mask image; instance i = (cls, mask id = cls_indexes_old[i] + 1, projected centre, z)
+// owns the pixels with mask == id AND label == cls.  The reference loops the instances in order and overwrites, so the
+// LAST matching instance wins.  instances [B, I, 5] = (cls, mask_id, cx, cy, z); z <= 0 marks an unused slot.
+__global__ void __launch_bounds__(256)
+k_vertex_targets_instances(const int* __restrict__ label, const int* __restrict__ mask, const float* __restrict__ inst, unsigned npix,
+                           int HW, int W, int C, int I, float w_inside, float* __restrict__ targets, float* __restrict__ weights)
+{
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        const int l = __ldg(label + pix);
+        if (l <= 0 || l >= C) continue;
+        const int m = __ldg(mask + pix);
+        const int b = pix / HW, p = pix - b * HW;
+        const float* rows = inst + (size_t)b * I * 5;
+        int hit = -1;
+        for (int i = 0; i < I; i++)
+            if (rows[5 * i + 4] > 0.f && (int)rows[5 * i] == l && (int)rows[5 * i + 1] == m) hit = i;
+        if (hit < 0) continue;
+        const float* r = rows + 5 * hit;
+        const double dx = (double)r[2] - (double)(p % W), dy = (double)r[3] - (double)(p / W);
+        const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+        const size_t o = (size_t)pix * 3 * C + 3 * l;
+        targets[o] = (float)(dx / nrm); targets[o + 1] = (float)(dy / nrm); targets[o + 2] = (float)log((double)r[4]);
+        weights[o] = w_inside; weights[o + 1] = w_inside; weights[o + 2] = w_inside;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pose blob and meta_data packing of the data layer (minibatch.py:440-451, 474-492):
+//   pose_blob rows [image, cls, 0, 0, 0, 0, mat2quat(R) (w, x, y, z), T] for every listed instance, images in order;
+//   meta_data[48]: K * im_scale with K[2][2] = 1 in [0:9], its (pseudo-)inverse in [9:18], zeros elsewhere, FLIP_X signs.
+// mat2quat is transforms3d's (Bar-Itzhack): eigenvector of the largest eigenvalue of the symmetric 4x4 K matrix, here
+// by cyclic Jacobi rotations in double, w made non-negative.
+// ---------------------------------------------------------------------------------------------
+__device__ void mat2quat_d(const float* __restrict__ rt /*3x4 row-major*/, float q[4])
+{
+    const double Qxx = rt[0], Qxy = rt[1], Qxz = rt[2], Qyx = rt[4], Qyy = rt[5], Qyz = rt[6], Qzx = rt[8], Qzy = rt[9], Qzz = rt[10];
+    double A[4][4] = {{Qxx - Qyy - Qzz, Qyx + Qxy, Qzx + Qxz, Qyz - Qzy},
+                      {Qyx + Qxy, Qyy - Qxx - Qzz, Qzy + Qyz, Qzx - Qxz},
+                      {Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, Qxy - Qyx},
+                      {Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz}};
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) A[i][j] /= 3.0;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0;
+        for (int i = 0; i < 4; i++)
+            for (int j = i + 1; j < 4; j++) off += A[i][j] * A[i][j];
+        if (off < 1e-30) break;
+        for (int pI = 0; pI < 3; pI++)
+            for (int qI = pI + 1; qI < 4; qI++) {
+                if (fabs(A[pI][qI]) < 1e-300) continue;
+                const double theta = (A[qI][qI] - A[pI][pI]) / (2.0 * A[pI][qI]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; k++) {
+                    const double akp = A[k][pI], akq = A[k][qI];
+                    A[k][pI] = c * akp - sn * akq; A[k][qI] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 4; k++) {
+                    const double apk = A[pI][k], aqk = A[qI][k];
+                    A[pI][k] = c * apk - sn * aqk; A[qI][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 4; k++) {
+                    const double vkp = V[k][pI], vkq = V[k][qI];
+                    V[k][pI] = c * vkp - sn * vkq; V[k][qI] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int k = 1; k < 4; k++)
+        if (A[k][k] > A[best][best]) best = k;
+    double w = V[3][best], x = V[0][best], y = V[1][best], z = V[2][best];   // vecs[[3, 0, 1, 2], argmax]
+    if (w < 0) { w = -w; x = -x; y = -y; z = -z; }
+    q[0] = (float)w; q[1] = (float)x; q[2] = (float)y; q[3] = (float)z;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_pose_meta(const float* __restrict__ poses /*[B,I,12]*/, const int* __restrict__ cls /*[B,I], < 0 = unused*/,
+                 const float* __restrict__ intr /*[B,9]*/, int B, int I, float im_scale, int flip_x, float* __restrict__ pose_blob /*[B*I,13]*/,
+                 int* __restrict__ num_rows, float* __restrict__ meta /*[B,48]*/)
+{
+    __shared__ int s_off[1025];
+    const int t = threadIdx.x, n = B * I;
+    if (t == 0) {
+        int run = 0;
+        for (int k = 0; k < n; k++) { s_off[k] = run; run += cls[k] >= 0 ? 1 : 0; }
+        s_off[n] = run;
+        *num_rows = run;
+    }
+    __syncthreads();
+    for (int k = t; k < n; k += blockDim.x) {
+        float* row = pose_blob + (size_t)k * 13;
+        if (k >= s_off[n])
+            for (int j = 0; j < 13; j++) row[j] = 0.f;      // rows beyond the count are zero (capacity buffer)
+    }
+    __syncthreads();
+    for (int k = t; k < n; k += blockDim.x) {
+        if (cls[k] < 0) continue;
+        const float* rt = poses + (size_t)k * 12;
+        float* row = pose_blob + (size_t)s_off[k] * 13;
+        row[0] = (float)(k / I); row[1] = (float)cls[k];
+        row[2] = row[3] = row[4] = row[5] = 0.f;            // box: "fill later" (minibatch.py:447)
+        mat2quat_d(rt, row + 6);
+        row[10] = rt[3]; row[11] = rt[7]; row[12] = rt[11];
+    }
+    for (int b = t; b < B; b += blockDim.x) {
+        float* m = meta + (size_t)b * 48;
+        for (int j = 0; j < 48; j++) m[j] = 0.f;
+        double K[9];
+        for (int j = 0; j < 9; j++) K[j] = (double)(float)(intr[b * 9 + j]) * (double)im_scale;
+        K[8] = 1.0;
+        // inverse by cofactors (np.linalg.pinv of the non-singular 3x3; agreement 1e-6 relative after the float32 cast)
+        const double c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+        const double det = K[0] * c00 + K[1] * c01 + K[2] * c02;
+        double Ki[9] = {c00 / det, (K[2] * K[7] - K[1] * K[8]) / det, (K[1] * K[5] - K[2] * K[4]) / det,
+                        c01 / det, (K[0] * K[8] - K[2] * K[6]) / det, (K[2] * K[3] - K[0] * K[5]) / det,
+                        c02 / det, (K[1] * K[6] - K[0] * K[7]) / det, (K[0] * K[4] - K[1] * K[3]) / det};
+        for (int j = 0; j < 9; j++) { m[j] = (float)K[j]; m[9 + j] = (float)Ki[j]; }
+        if (flip_x) { m[0] = -m[0]; m[9] = -m[9]; m[11] = -m[11]; }   // minibatch.py:488-491
+    }
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 k_vertex_loss_fused(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW,
                     int W, int C, float w_inside, float sigma2, double* __restrict__ partial, unsigned* __restrict__ ticket,
@@ -310,4 +433,27 @@ extern "C" int pcnn_smooth_l1_vertex_fwd(const float* pred, const float* targets
         k_smooth_l1_vertex_grad<<<kNumSMs * 16, 256, 0, (cudaStream_t)stream>>>(pred, targets, weights, n, sigma * sigma, loss_out, upstream,
                                                                                   grad_pred);
     return check_launch("smooth_l1_vertex");
+}
+
+extern "C" int pcnn_vertex_targets_instances_fwd(const int32_t* label, const int32_t* mask, const float* instances, int B, int H, int W,
+                                                 int C, int I, float w_inside, float* targets, float* weights, void* stream)
+{
+    PCNN_REQUIRE(label && mask && instances && targets && weights, "vertex_targets_instances: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && I >= 1, "vertex_targets_instances: bad shape");
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "vertex_targets_instances: too many pixels");
+    const unsigned npix = (unsigned)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(targets, 0, sizeof(float) * (size_t)npix * 3 * C, st);
+    cudaMemsetAsync(weights, 0, sizeof(float) * (size_t)npix * 3 * C, st);
+    k_vertex_targets_instances<<<kNumSMs * 16, 256, 0, st>>>(label, mask, instances, npix, H * W, W, C, I, w_inside, targets, weights);
+    return check_launch("vertex_targets_instances");
+}
+
+extern "C" int pcnn_pack_pose_meta_fwd(const float* poses, const int32_t* cls, const float* intrinsics, int B, int I, float im_scale,
+                                       int flip_x, float* pose_blob, int32_t* num_rows, float* meta, void* stream)
+{
+    PCNN_REQUIRE(poses && cls && intrinsics && pose_blob && num_rows && meta, "pack_pose_meta: NULL tensor pointer");
+    PCNN_REQUIRE(B >= 1 && I >= 1 && B * I <= 1024, "pack_pose_meta: at most 1024 instance slots per batch (got %d x %d)", B, I);
+    k_pack_pose_meta<<<1, 256, 0, (cudaStream_t)stream>>>(poses, cls, intrinsics, B, I, im_scale, flip_x, pose_blob, num_rows, meta);
+    return check_launch("pack_pose_meta");
 }

@@ -33,6 +33,39 @@ def generate_vertex_targets(im_label, centers, w_inside=1.0):
     return targets, weights
 
 
+def generate_vertex_targets_instances(im_label, mask, instances, num_classes, w_inside=1.0):
+    """Multi-instance branch of _generate_vertex_targets (minibatch.py:549-573): im_label / mask [B,H,W] int32 (instance
+    mask image), instances [B,I,5] f32 = (cls, mask id = cls_indexes_old + 1, cx, cy, z), z <= 0 = unused slot."""
+    lab = require_cuda("im_label", im_label, torch.int32, 3)
+    msk = require_cuda("mask", mask, torch.int32, 3)
+    ins = require_cuda("instances", instances, torch.float32, 3)
+    B, H, W = lab.shape
+    if msk.shape != lab.shape or ins.shape[0] != B or ins.shape[2] != 5:
+        raise ValueError("mask must match im_label and instances must be [B,I,5]")
+    C = int(num_classes)
+    targets = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=lab.device)
+    weights = torch.empty_like(targets)
+    check(lib().pcnn_vertex_targets_instances_fwd(ptr(lab), ptr(msk), ptr(ins), B, H, W, C, ins.shape[1], f32(w_inside), ptr(targets),
+                                                  ptr(weights), stream()))
+    return targets, weights
+
+
+def pack_pose_meta(poses, cls, intrinsics, im_scale=1.0, flip_x=False):
+    """The data layer's pose blob and meta_data packing on the device (minibatch.py:440-451, 474-492): poses [B,I,3,4] f32
+    ([R|T] per listed instance), cls [B,I] int32 (< 0 = unused slot), intrinsics [B,3,3] f32 -> (pose_blob capacity buffer
+    [B*I,13], num_rows [1] int32 on the device, meta_data [B,1,1,48])."""
+    po = require_cuda("poses", poses, torch.float32, 4)
+    cl = require_cuda("cls", cls, torch.int32, 2)
+    kk = require_cuda("intrinsics", intrinsics, torch.float32, 3)
+    B, I = cl.shape
+    blob = torch.empty((B * I, 13), dtype=torch.float32, device=po.device)
+    nrows = torch.empty((1,), dtype=torch.int32, device=po.device)
+    meta = torch.empty((B, 1, 1, 48), dtype=torch.float32, device=po.device)
+    check(lib().pcnn_pack_pose_meta_fwd(ptr(po), ptr(cl), ptr(kk), B, I, f32(im_scale), int(bool(flip_x)), ptr(blob), ptr(nrows), ptr(meta),
+                                        stream()))
+    return blob, nrows, meta
+
+
 def loss_cross_entropy_hard(scores, prob, gt_label, threshold, want_grad=False, upstream=1.0):
     """-sum(hard_label(prob, gt, threshold) * scores) / (sum(mask) + 1e-10) with scores = log-softmax [B,H,W,C];
     the mask is never materialised.  Returns (loss [1] view, count [1] view[, grad wrt scores])."""

@@ -96,3 +96,27 @@ def vertex_target_inputs(seed=41, H=60, W=80, C=6, B=2):
             centers[0, classes[1], 0:2] = (17.0, 23.0)   # integer centre on a pixel: zero vector / (0 + 1e-10)
             label[0, 23, 17] = classes[1]
     return label, centers
+
+
+def vertex_target_multi_inputs(seed=43, H=60, W=80, C=6, B=2, I=5):
+    """Multi-instance images (minibatch.py:425-431): two instances of one class told apart by an instance-mask image.
+    Returns label [B,H,W] int32, mask [B,H,W] int32 and instances [B,I,5] f32 = (cls, mask id, cx, cy, z); z = 0 marks an
+    unused slot.  Image 0 also has an instance whose mask region carries a DIFFERENT label (no pixels: skipped) and a
+    repeated (cls, id) pair (the later instance overwrites the earlier one)."""
+    rng = np.random.default_rng(seed)
+    label = np.zeros((B, H, W), np.int32)
+    mask = np.zeros((B, H, W), np.int32)
+    inst = np.zeros((B, I, 5), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        classes = [2, 2, 4, 1][: I - 1]                         # class 2 twice
+        for i, c in enumerate(classes):
+            cx, cy = rng.uniform(0.15 * W, 0.85 * W), rng.uniform(0.15 * H, 0.85 * H)
+            a, bb = rng.uniform(6, 12), rng.uniform(6, 12)
+            region = ((xx - cx) / a) ** 2 + ((yy - cy) / bb) ** 2 <= 1
+            label[b][region] = c
+            mask[b][region] = i + 1                               # cls_indexes_old[i] + 1
+            inst[b, i] = (c, i + 1, cx + rng.normal(0, 2), cy + rng.normal(0, 2), rng.uniform(0.5, 1.5))
+    label[0][mask[0] == 4] = 3                                    # instance 3 (class 1): its mask region is labelled 3 -> no pixels
+    inst[0, 4] = inst[0, 0]; inst[0, 4, 2:5] = (33.0, 21.0, 1.25)  # same (cls, id) as instance 0, listed later: it wins
+    return label, mask, inst

@@ -44,6 +44,21 @@ def main():
         fn(label[b], listed, center, poses, C, None, None, None, False, None, targets[b], weights[b])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "vertex_targets.npz"), targets=targets, weights=weights)
     print("targets nonzero", int((targets != 0).sum()), "weights nonzero", int((weights != 0).sum()))
+    # multi-instance branch (minibatch.py:549-573): same function, is_multi_instances = 1
+    label, mask, inst = cases.vertex_target_multi_inputs()
+    B, H, W = label.shape
+    targets = np.zeros((B, H, W, 3 * C), np.float32)
+    weights = np.zeros((B, H, W, 3 * C), np.float32)
+    for b in range(B):
+        rows = [r for r in inst[b] if r[4] > 0]
+        cls_indexes = np.array([r[0] for r in rows], dtype=np.float32)
+        cls_indexes_old = np.array([r[1] - 1 for r in rows], dtype=np.float32)
+        center = np.array([[r[2], r[3]] for r in rows], dtype=np.float32)
+        poses = np.zeros((3, 4, len(rows)), np.float32)
+        poses[2, 3, :] = [r[4] for r in rows]
+        fn(label[b], cls_indexes, center, poses, C, None, None, mask[b], True, cls_indexes_old, targets[b], weights[b])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "vertex_targets_multi.npz"), targets=targets, weights=weights)
+    print("multi-instance: targets nonzero", int((targets != 0).sum()), "weights nonzero", int((weights != 0).sum()))
 
 
 if __name__ == "__main__":

@@ -173,3 +173,52 @@ def test_vertex_loss_fused_equals_materialised(cuda):
         assert torch.equal(g0, g1)
         want, _ = oracle.smooth_l1_loss_vertex(to_np(pred), to_np(vt), to_np(vw), sigma)
         assert abs(float(l1.item()) - want) <= 1e-5 * abs(want)
+
+
+def test_multi_instance_vertex_targets_match_reference_golden(cuda):
+    """pcnn_vertex_targets_instances_fwd vs the reference function's own output on the multi-instance branch
+    (minibatch.py:549-573; tests/golden/vertex_targets_multi.npz): direction components bit-exact, log z to 1 ulp of libm."""
+    from tests.golden import cases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vertex_targets_multi.npz"))
+    label, mask, inst = cases.vertex_target_multi_inputs()
+    t, w = train_ops.generate_vertex_targets_instances(T(label, cuda), T(mask, cuda), T(inst, cuda), 6, 10.0)
+    t, w = t.cpu().numpy(), w.cpu().numpy()
+    np.testing.assert_array_equal(w, g["weights"])
+    xy = np.ones(t.shape[-1], bool); xy[2::3] = False
+    np.testing.assert_array_equal(t[..., xy], g["targets"][..., xy])
+    np.testing.assert_allclose(t[..., ~xy], g["targets"][..., ~xy], rtol=2e-7, atol=0)
+
+
+def test_pack_pose_meta_matches_data_layer_restatement(cuda):
+    """pcnn_pack_pose_meta_fwd vs oracle.pack_pose_meta (minibatch.py:440-451, 474-492): row order / class / image columns
+    exact, quaternions (Jacobi vs LAPACK eigh) and translations 1e-6, meta_data 1e-6 relative (cofactor inverse vs pinv)."""
+    from scipy.spatial.transform import Rotation
+    from posecnn_b200 import synth
+    rng = np.random.default_rng(9)
+    B, I = 3, 5
+    poses = np.zeros((B, I, 3, 4), np.float32)
+    cls = -np.ones((B, I), np.int32)
+    for b in range(B):
+        n = [4, 0, 5][b]
+        cls[b, :n] = rng.integers(1, 22, n)
+        for j in range(n):
+            poses[b, j, :, :3] = Rotation.from_quat(rng.normal(size=4)).as_matrix()
+            poses[b, j, :, 3] = rng.uniform(-0.3, 1.2, 3)
+    poses[0, 1, :, :3] = np.eye(3)                                          # identity rotation: degenerate eigenproblem
+    poses[0, 2, :, :3] = Rotation.from_euler("z", 180, degrees=True).as_matrix()   # w = 0 boundary
+    K = np.stack([synth.intrinsics(480, 640)] * B).astype(np.float32)
+    for scale, flip in ((1.0, False), (0.5, True)):
+        blob, nrows, meta = train_ops.pack_pose_meta(T(poses, cuda), T(cls, cuda), T(K, cuda), scale, flip)
+        wb, wm = oracle.pack_pose_meta(poses, cls, K, scale, flip)
+        n = int(nrows.item())
+        assert n == wb.shape[0] == 9
+        got = blob.cpu().numpy()
+        assert not got[n:].any()
+        np.testing.assert_array_equal(got[:n, :6], wb[:, :6])
+        for a, b_ in zip(got[:n], wb):
+            qa, qb = a[6:10], b_[6:10]
+            if abs(qb[0]) < 1e-6:            # w = 0: the sign of the axis is arbitrary in both implementations
+                qa = qa * np.sign(np.dot(qa, qb))
+            np.testing.assert_allclose(qa, qb, atol=2e-6)
+        np.testing.assert_allclose(got[:n, 10:], wb[:, 10:], atol=0)
+        np.testing.assert_allclose(meta.cpu().numpy().reshape(B, 48), wm, rtol=1e-6, atol=1e-9)
