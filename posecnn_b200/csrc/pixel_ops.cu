@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pcnn {
@@ -610,6 +612,119 @@ k_voxel_average_wide(const float* __restrict__ src, const float* __restrict__ de
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// BackprojectForward fused (backprojecting_op_gpu.cu.cc:16-126): ONE kernel writes top_data, top_flag and top_label.
+// A CTA owns a slab of kBpVox consecutive voxels of one image:
+//   phase 1  one thread per voxel: voxel -> pixel projection and the (2k+1)^2 depth tests ONCE per voxel (the separate
+//            data / label launches with one thread per 16 channels repeated them 5 times); count, (px, py, Z1) -> smem;
+//   phase 2  all threads stream the slab's three contiguous output regions with 128-bit stores (data: Cf floats per
+//            voxel, flag likewise, label: C floats per voxel): voxels without a hit (almost all of the grid) are pure
+//            stores — zeros, zeros, and the label_3d copy; the few voxels with hits re-walk their window in the
+//            reference's order (x outer, y inner) and average.
+// The op is write-bound: B * G^3 * (2 Cf + C) * 4 bytes out, B * G^3 * C * 4 + the touched pixels in.
+// ----------------------------------------------------------------------------------------
+constexpr int kBpVox = 64;
+
+__global__ void __launch_bounds__(256)
+k_backproject_fused(const float* __restrict__ data, const float* __restrict__ label, const float* __restrict__ depth,
+                    const float* __restrict__ meta_all, const float* __restrict__ label_3d, int H, int W, int Cf, int C, int num_meta,
+                    int G, int ks, float threshold, float* __restrict__ top_data, float* __restrict__ top_label,
+                    float* __restrict__ top_flag)
+{
+    __shared__ int s_cnt[kBpVox], s_px[kBpVox], s_py[kBpVox];
+    __shared__ float s_z[kBpVox];
+    const int n = blockIdx.y, t = threadIdx.x;
+    const unsigned G3 = (unsigned)G * G * G;
+    const unsigned v0 = blockIdx.x * kBpVox;
+    const int nvox = (int)min((unsigned)kBpVox, G3 - v0);
+    const float* m = meta_all + (size_t)n * num_meta;
+    const float* dep = depth + (size_t)n * H * W;
+    if (t < nvox) {
+        const unsigned vl = v0 + t;
+        const int w = (int)(vl % G), h = (int)((vl / G) % G), d = (int)(vl / ((unsigned)G * G));
+        int px, py;
+        float Z1;
+        voxel_to_pixel(m, d, h, w, px, py, Z1);
+        int count = 0;
+        const int x0 = max(px - ks, 0), x1 = min(px + ks, W - 1);
+        const int y0 = max(py - ks, 0), y1 = min(py + ks, H - 1);
+        for (int x = x0; x <= x1; x++)
+            for (int y = y0; y <= y1; y++)
+                if (fabsf(__fsub_rn(__ldg(dep + (size_t)y * W + x), Z1)) < threshold) count++;
+        s_cnt[t] = count; s_px[t] = px; s_py[t] = py; s_z[t] = Z1;
+    }
+    __syncthreads();
+    const size_t vbase = (size_t)n * G3 + v0;
+    // ---- top_data / top_flag: Cf / 4 float4 per voxel
+    {
+        const int q4 = Cf >> 2;
+        float4* od = reinterpret_cast<float4*>(top_data + vbase * Cf);
+        float4* of = reinterpret_cast<float4*>(top_flag + vbase * Cf);
+        const float* src = data + (size_t)n * H * W * Cf;
+        for (int i = t; i < nvox * q4; i += 256) {
+            const int v = i / q4, g = i - v * q4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float fl = 0.f;
+            const int cnt = s_cnt[v];
+            if (cnt > 0) {
+                const int px = s_px[v], py = s_py[v];
+                const float Z1 = s_z[v];
+                const int x0 = max(px - ks, 0), x1 = min(px + ks, W - 1);
+                const int y0 = max(py - ks, 0), y1 = min(py + ks, H - 1);
+                for (int x = x0; x <= x1; x++)
+                    for (int y = y0; y <= y1; y++) {
+                        const size_t pix = (size_t)y * W + x;
+                        if (fabsf(__fsub_rn(__ldg(dep + pix), Z1)) < threshold) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(src + pix * Cf) + g);
+                            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+                        }
+                    }
+                const float cf = (float)cnt;
+                acc.x = __fdiv_rn(acc.x, cf); acc.y = __fdiv_rn(acc.y, cf); acc.z = __fdiv_rn(acc.z, cf); acc.w = __fdiv_rn(acc.w, cf);
+                fl = 1.f;
+            }
+            st_stream_f4(od + i, acc);
+            st_stream_f4(of + i, make_float4(fl, fl, fl, fl));
+        }
+    }
+    // ---- top_label: C floats per voxel; the slab's nvox * C floats are contiguous (float4 path when the slab is 16-byte
+    // aligned and whole: kBpVox * C * 4 bytes is a multiple of 16 for every C)
+    {
+        float* ol = top_label + vbase * C;
+        const float* l3 = label_3d + vbase * C;
+        const float* src = label + (size_t)n * H * W * C;
+        const int total = nvox * C;
+        auto element = [&](int i) -> float {
+            const int v = i / C, c = i - v * C;
+            const int cnt = s_cnt[v];
+            if (cnt == 0) return __ldg(l3 + i);
+            const int px = s_px[v], py = s_py[v];
+            const float Z1 = s_z[v];
+            const int x0 = max(px - ks, 0), x1 = min(px + ks, W - 1);
+            const int y0 = max(py - ks, 0), y1 = min(py + ks, H - 1);
+            float acc = 0.f;
+            for (int x = x0; x <= x1; x++)
+                for (int y = y0; y <= y1; y++) {
+                    const size_t pix = (size_t)y * W + x;
+                    if (fabsf(__fsub_rn(__ldg(dep + pix), Z1)) < threshold) acc += __ldg(src + pix * C + c);
+                }
+            return __fdiv_rn(acc, (float)cnt);
+        };
+        if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(ol) | reinterpret_cast<uintptr_t>(l3)) & 15) == 0) {
+            for (int i4 = t; i4 < total / 4; i4 += 256) {
+                const int i = 4 * i4;
+                const int va = i / C, vb = (i + 3) / C;
+                float4 o;
+                if (s_cnt[va] == 0 && s_cnt[vb] == 0) o = ld_stream_f4(reinterpret_cast<const float4*>(l3) + i4);
+                else o = make_float4(element(i), element(i + 1), element(i + 2), element(i + 3));
+                st_stream_f4(reinterpret_cast<float4*>(ol) + i4, o);
+            }
+        } else {
+            for (int i = t; i < total; i += 256) ol[i] = element(i);
+        }
+    }
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace pcnn
@@ -754,6 +869,17 @@ extern "C" int pcnn_backproject_fwd(const float* data, const float* label, const
     PCNN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Cf >= 1 && C >= 1, "backproject: bad shape");
     if (grid_size == 0) return PCNN_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const size_t G3 = (size_t)grid_size * grid_size * grid_size;
+        static const bool fused_on = getenv("PCNN_BACKPROJECT_FUSED") == nullptr || atoi(getenv("PCNN_BACKPROJECT_FUSED")) != 0;
+        if (fused_on && Cf % 4 == 0 && aligned16(data) && aligned16(top_data) && aligned16(top_flag) && B <= 65535 &&
+            G3 * (size_t)(Cf > C ? Cf : C) < 0x7fffffffULL) {
+            dim3 grid((unsigned)((G3 + kBpVox - 1) / kBpVox), B);
+            k_backproject_fused<<<grid, 256, 0, st>>>(data, label, depth, meta, label_3d, H, W, Cf, C, num_meta, grid_size, kernel_size,
+                                                      threshold, top_data, top_label, top_flag);
+            return check_launch("backproject (fused)");
+        }
+    }
     int rc = launch_average(data, depth, meta, nullptr, B, H, W, Cf, num_meta, grid_size, kernel_size, threshold, top_data,
                             top_flag, st);
     if (rc) return rc;

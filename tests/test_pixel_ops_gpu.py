@@ -57,7 +57,7 @@ def test_hard_label(cuda, C):
     assert gp.shape == (2, 37, 53, C) and gg.shape == (2, 37, 53) and not gp.any() and not gg.any()
 
 
-@pytest.mark.parametrize("Cf,C,G", [(64, 22, 32), (6, 3, 16)])
+@pytest.mark.parametrize("Cf,C,G", [(64, 22, 32), (6, 3, 16), (8, 3, 128)])   # G = 128: the SURVEY 8(d) primary grid
 def test_project_backproject(cuda, Cf, C, G):
     from posecnn_b200.backprojecting_layer import backprojecting_op as bop
     from posecnn_b200.projecting_layer import projecting_op as pop

@@ -57,6 +57,22 @@ for nm, h, w, sc in (("conv5_3", 30, 40, 1 / 16.0), ("conv4_3", 60, 80, 1 / 8.0)
     top, arg = rop.roi_pool(f32, rois, 7, 7, sc, 0); g = torch.randn_like(top)
     ms = timeit(lambda: rop.roi_pool_grad(f32, rois, arg, g, 7, 7, sc, 0)); report(f"roi_pool bwd {nm} N128", ms, B * h * w * 512 * 4 + out_b, "dense grad write + pooled reads")
     del f32, bf
+# pose head (csrc/fc_tc.cu): fused RoiPool pair -> fc6 -> fc7 -> fc8 at 128 ROI rows; weight streaming, HBM bound
+from posecnn_b200 import pose_head
+f5 = torch.randn((B, 30, 40, 512), device=dev).to(torch.bfloat16); f4 = torch.randn((B, 60, 80, 512), device=dev).to(torch.bfloat16)
+r = rois.cpu().numpy(); area = 0
+for (h, w, sc) in ((30, 40, 1 / 16.0), (60, 80, 1 / 8.0)):
+    for x1, y1, x2, y2 in r[:, 2:6]:
+        area += max((min(round(x2 * sc), w - 1) - max(round(x1 * sc), 0) + 1) * (min(round(y2 * sc), h - 1) - max(round(y1 * sc), 0) + 1), 0)
+ms = timeit(lambda: pose_head.roi_pool_pair(f5, f4, rois)); report("roi_pool_pair bf16 (conv5_3 + conv4_3) N128", ms, area * 512 * 2 + 128 * 49 * 512 * 2, "touched bin areas + bf16 fc6 operand")
+xa = pose_head.roi_pool_pair(f5, f4, rois)
+for nm, K, N in (("fc6", 25088, 4096), ("fc7", 4096, 4096), ("fc8", 4096, 88)):
+    wt = pose_head.fc_weights_to_tc(torch.randn((K, N), device=dev) * 0.01); bs = torch.zeros(N, device=dev)
+    a = xa if K == 25088 else torch.randn((128, K), device=dev).to(torch.bfloat16)
+    ms = timeit(lambda: pose_head.fc(a, wt, bs, "relu" if N > 88 else "tanh", torch.bfloat16 if N > 88 else torch.float32))
+    report(f"{nm} 128 x {K} x {N} bf16 (split-K tcgen05 + finish)", ms, wt.numel() * 2 + 128 * K * 2 + 128 * N * 4, "weights + A + out; 2*M*K*N = %.1f GFLOP" % (2 * 128 * K * N / 1e9))
+    del wt
+del f5, f4, xa
 # Project / Backproject, G = 128, Cf = 64, batch 4 (8.6 GB of voxel grids at batch 4)
 Bp, G, Cf = 4, 128, 64
 case = synth.make_projection_case(Bp, H, W, Cf, 3, 8, seed=5)  # small grid for meta only
@@ -74,4 +90,9 @@ pred, targ, wt = [torch.from_numpy(a).to(dev) for a in synth.make_pose_batch(576
 ms = timeit(lambda: aop.average_distance_loss(pred, targ, wt, pts, sym, 0.01))
 nsym = int(sum(1 for n in range(576) if wt[n].any() and sym[int(torch.argmax(wt[n])) // 4] > 0))
 report("average_distance fwd N576 P2620", ms, 576 * 4 * C * 12 + C * 2620 * 12, f"{nsym} symmetric rois (O(P^2) closest-point search, compute bound)")
+nact = int(sum(1 for n in range(576) if wt[n].any()))
+flop = (nact - nsym) * 2620 * 60.0 + nsym * 2620.0 * 2620.0 * 20.0      # non-sym N*P*~60, sym N*P^2*~20
+fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                               # CUDA-core fp32 FMA peak at the max SM clock, TFLOP/s
+rows[-1].update(flop=flop, tflops=flop / ms / 1e9, frac_of_fp32_peak=flop / ms / 1e9 / fp32_peak)
+print(f"  average_distance FLOP view: {flop/1e9:.2f} GFLOP ({nsym} symmetric of {nact} active rois) -> {flop/ms/1e9:.2f} TFLOP/s = {flop/ms/1e9/fp32_peak*100:.1f}% of the {fp32_peak:.1f} TFLOP/s fp32 CUDA-core peak")
 json.dump(rows, open(os.path.join(os.path.dirname(__file__), "..", "gpurun_out", "bench_ops.json"), "w"), indent=1)
