@@ -500,7 +500,7 @@ def run_full(args, rank, world, local, input_format="COLOR"):
         value=Bg / (ms_step * 1e-3),
         unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True,
         scaling="strong", vs_baseline=None,
-        dtype="bf16 operands / fp32 accumulate (conv stack, 1x1 heads, fc6-fc8), fp32 / int32 elsewhere",
+        dtype="bf16 operands / fp32 accumulate (conv stack, 1x1 heads), fp16 operands / fp32 accumulate (fc6-fc8), fp32 / int32 elsewhere",
         data="synthetic",
         config=dict(workload=("configs[2]: full VGG16+Hough+ROI inference" if input_format == "COLOR" else
                               "configs[3] network: RGB-D two-trunk VGG16+Hough+ROI inference") +

@@ -191,24 +191,50 @@ int pcnn_conv1_depth_fused_tc(const float* depth, const float* mean3_host, const
 int pcnn_maxpool2x2_bf16(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Backward pass of the convolution / fully connected layers for the training step (lib/fcn/train.py:206-260 drives
+ * TensorFlow's gradients of Network.conv / Network.fc / Network.max_pool, networks/network.py:159-188, 303-310, 392-422):
+ *   dz = dy * [y > 0];  dW[r,s,ci,co] = sum_{n,h,w} x[n,h+r-1,w+s-1,ci] * dz[n,h,w,co];  db = sum dz;
+ *   dx = conv(dz, W flipped and transposed) = pcnn_conv_bf16_tc on conv.hwio_to_tc_dgrad weights.
+ *  pcnn_conv_wgrad_bf16_tc   weight gradient on tcgen05 with BOTH operands MN-major (the reduction index = pixel is the row of
+ *      the NHWC activation tiles as TMA delivers them: no transposed copies), split-K over pixel ranges with a fixed-order
+ *      reduction; x [B,H,W,Cin], dz [B,H,W,Cout] bf16 -> dW [Cout][ksize*ksize*Cin] f32 (the tensor-core weight layout) =
+ *      scale * gradient (+ decay * w when w != NULL: the l2_regularizer term, network.py:171-172).  A fully connected layer is
+ *      the 1x1 case with B = H = 1, W = rows.  Cin, Cout multiples of 64.
+ *  pcnn_relu_bwd_bf16 / pcnn_maxpool_relu_bwd_bf16   dz from the upstream gradient and the layer's stored output (ReLU mask;
+ *      2x2/2 max-pool routing to the window's first maximum fused with the mask of the conv below), optionally the bias
+ *      gradient db [C] = scale * sum_pixels dz (+ decay * b) through per-CTA partials in bias_ws (pcnn_bias_ws_bytes).
+ *  pcnn_add_to_bf16          gradient fan-in: out = a + b (+ b_f32), bf16 out.
+ */
+int pcnn_conv_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, size_t* bytes);
+int pcnn_conv_wgrad_bf16_tc(const void* x_bf16, const void* dz_bf16, int B, int H, int W, int Cin, int Cout, int ksize,
+                            float scale, const float* w_f32, float decay, float* dW, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int pcnn_bias_ws_bytes(int C, size_t* bytes);
+int pcnn_relu_bwd_bf16(const void* g_bf16, const void* y_bf16, size_t npix, int C, int has_relu, void* dz_bf16, float scale,
+                       const float* b, float decay, float* db, void* bias_ws, size_t bias_ws_bytes, void* stream);
+int pcnn_maxpool_relu_bwd_bf16(const void* g_bf16, const void* y_bf16, int B, int H, int W, int C, void* dz_bf16, float scale,
+                               const float* b, float decay, float* db, void* bias_ws, size_t bias_ws_bytes, void* stream);
+int pcnn_add_to_bf16(const void* a_bf16, const void* b_bf16, const float* b_f32, size_t n, void* out_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pose-regression head (networks/vgg16_convs.py:177-197, Network.fc networks/network.py:392-422, tanh :436-438) on own
  * kernels (csrc/fc_tc.cu); inference path (no argmax, no gradients).
- *  pcnn_roi_pool_pair_bf16  pool_score = RoiPool(conv5_3, scale5) + RoiPool(conv4_3, scale4) with the RoiPool rule of
- *      roi_pooling_layer/roi_pooling_op_gpu.cu.cc:19-101, added in fp32 and written as the bf16 fc6 operand
+ *  pcnn_roi_pool_pair_f16  pool_score = RoiPool(conv5_3, scale5) + RoiPool(conv4_3, scale4) with the RoiPool rule of
+ *      roi_pooling_layer/roi_pooling_op_gpu.cu.cc:19-101, added in fp32 and written as the fp16 fc6 operand
  *      [num_rois, pooled_h*pooled_w*C] in (h, w, c) order.  f5 [B,H5,W5,C], f4 [B,H4,W4,C] bf16 NHWC; rois
  *      [num_rois, roi_stride] f32 rows [batch, cls, x1,y1,x2,y2,...]; the image index is rois[:,0] - batch_offset
  *      (image shards carry global batch indices); an index outside [0, B) pools nothing (zeros).
- *  pcnn_fc_bf16_tc          out = act(A[M,K] @ W[N,K]^T + bias): tcgen05 GEMM, BF16 operands, FP32 accumulation, split-K
- *      over the grid with a fixed-order reduction (deterministic); A, W bf16 row-major with K contiguous, N % 128 == 0,
- *      K % 64 == 0; rows n_valid..N of W are zero padding; act 0 none / 1 ReLU / 2 tanh; outputs: out_bf16 [M, ld_out]
+ *  pcnn_fc_f16_tc          out = act(A[M,K] @ W[N,K]^T + bias): tcgen05 GEMM, FP16 operands (11-bit mantissa: the 1e-3 quaternion tolerance), FP32 accumulation, split-K
+ *      over the grid with a fixed-order reduction (deterministic); A, W fp16 row-major with K contiguous, N % 128 == 0,
+ *      K % 64 == 0; rows n_valid..N of W are zero padding; act 0 none / 1 ReLU / 2 tanh; outputs: out_f16 [M, ld_out]
  *      (optional) and / or out_f32 [M, n_valid] (optional).  workspace: pcnn_fc_workspace_bytes(M, N, K).
  */
-int pcnn_roi_pool_pair_bf16(const void* f5_bf16, int H5, int W5, const void* f4_bf16, int H4, int W4, int C, int B,
+int pcnn_roi_pool_pair_f16(const void* f5_bf16, int H5, int W5, const void* f4_bf16, int H4, int W4, int C, int B,
                             int batch_offset, const float* rois, int num_rois, int roi_stride, int pooled_h,
-                            int pooled_w, float scale5, float scale4, void* out_bf16, void* stream);
+                            int pooled_w, float scale5, float scale4, void* out_f16, void* stream);
 int pcnn_fc_workspace_bytes(int M, int N, int K, size_t* bytes);
-int pcnn_fc_bf16_tc(const void* a_bf16, const void* w_bf16, const float* bias, int M, int N, int K, int n_valid, int act,
-                    void* out_bf16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes, void* stream);
+int pcnn_fc_f16_tc(const void* a_f16, const void* w_f16, const float* bias, int M, int N, int K, int n_valid, int act,
+                   void* out_f16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * FCN heads after the 1x1 convolutions on conv4_3 / conv5_3 (networks/vgg16_convs.py:128-163):
@@ -238,7 +264,8 @@ int pcnn_deconv_bilinear(const float* in, float* out, int B, int h, int w, int C
  *   greedy NMS in descending score order (ties: larger row index first = stable argsort reversed); a box is dropped
  *   when IoU(+1 convention, fp32) > thresh with a kept box of the same class (per_image = 1: and the same image; the
  *   reference ignores the batch column and only runs batch 1, per_image = 0 reproduces that);
- *   out_rois[k] = rois[keep[k]], out_poses[k] = [poses_pred[keep[k], 4c:4c+4] | poses_init[keep[k], 4:7]].
+ *   out_rois[k] = rois[keep[k]], out_poses[k] = [poses_pred[keep[k], 4c:4c+4] | poses_init[keep[k], 4:7]];
+ *   keep is in processing order (per_image = 1: image by image, ascending batch index, processing order inside an image).
  * rois [capacity,7], poses_init [capacity,7], poses_pred [capacity,4C] or NULL (then poses_init is passed through);
  * rows considered: max(*num_rois_dev, 1) when num_rois_dev != NULL (Hough's device row count; the reference always has
  * the dummy row), else num_rows.  Outputs are capacity buffers (rows beyond *num_keep are zero, keep = -1): no host

@@ -194,6 +194,8 @@ def nms(dets, thresh, per_image=False):
         if per_image:
             same &= img[rest] == img[i]
         order = rest[~((ovr > np.float32(thresh)) & same)]
+    if per_image:   # images are independent: emit them in batch order (processing order inside an image), like the op's batch loop
+        keep = sorted(keep, key=lambda k: int(img[k]))      # stable: keeps the processing order inside an image
     return keep
 
 

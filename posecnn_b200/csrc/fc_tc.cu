@@ -3,15 +3,19 @@
 // 25088 in (h, w, c) order, x @ W[in, out] + b, ReLU; tanh after fc8, network.py:436-438).
 //
 // At inference the head sees at most 128 ROI rows (MAX_ROI, hough_voting_gpu_op.cu.cc:14), so every layer is a
-// 128-row GEMM whose cost is streaming its weights once (fc6: 25088 x 4096 bf16 = 205 MB): HBM-bound.
+// 128-row GEMM whose cost is streaming its weights once (fc6: 25088 x 4096 fp16 = 205 MB): HBM-bound.
+// Operands are FP16, not BF16 like the trunk: K = 25088 products of 8-bit-mantissa operands leave ~5e-3 relative error on the
+// fc6 outputs (measured), 11-bit mantissas ~1e-3 — what the 1e-3 tolerance on the regressed quaternions needs (SURVEY.md
+// §8(c)); post-ReLU activations and Kaiming / trained weights sit well inside the fp16 range, and values saturate at 65504.
 //   k_roi_pool_pair   ONE kernel pools conv5_3 (scale 1/16) and conv4_3 (scale 1/8) with the RoiPool rule of
 //                     roi_pooling_op_gpu.cu.cc:19-101, adds them in fp32 (`pool_score`, vgg16_convs.py:183) and writes the
-//                     bf16 A operand [N, 25088] of fc6 directly (no fp32 pooled tensors, no argmax: inference only).
-//   k_fc_tc           D[128 rows, BN] partial = A[128, Kslice] * W[BN, Kslice]^T on tcgen05 (BF16 x BF16 -> FP32 in TMEM),
+//                     fp16 A operand [N, 25088] of fc6 directly (no fp32 pooled tensors, no argmax: inference only).
+//   k_fc_tc           D[128 rows, BN] partial = A[128, Kslice] * W[BN, Kslice]^T on tcgen05 (FP16 x FP16 -> FP32 in TMEM),
 //                     both operands K-major, TMA-fed through a 6-stage mbarrier ring; split-K over the grid so that
 //                     128 CTAs stream disjoint slices of the weight matrix; partials land in a small fp32 workspace.
-//   k_fc_finish       fixed-order sum of the split-K partials + bias + ReLU / tanh -> bf16 activation of the next layer
+//   k_fc_finish       fixed-order sum of the split-K partials + bias + ReLU / tanh -> fp16 activation of the next layer
 //                     (or the fp32 `poses_tanh`): run-to-run deterministic.
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "common.cuh"
@@ -80,7 +84,7 @@ k_fc_tc(const __grid_constant__ CUtensorMap map_a /*[M][K] bf16, box {64, 128}*/
         }
     } else if (warp == 5) {
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(kFcBN);
+            constexpr uint32_t idesc = make_idesc_f16(kFcBN);
             int stage = 0;
             uint32_t phase = 0;
             for (int c = 0; c < nchunks; c++) {
@@ -123,19 +127,33 @@ k_fc_tc(const __grid_constant__ CUtensorMap map_a /*[M][K] bf16, box {64, 128}*/
     if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// fp16 activations saturate instead of overflowing to inf (|x| <= 65504)
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
 // out[m][n] = act(bias[n] + sum_s partial[s][m][n]) for n < n_valid; act: 0 none, 1 ReLU, 2 tanh.
-// out_bf16 (row stride ld_out, the next layer's A operand) and / or out_f32 (row stride n_valid).
+// out_f16 (row stride ld_out, the next layer's A operand) and / or out_f32 (row stride n_valid).
 __global__ void __launch_bounds__(256)
 k_fc_finish(const float* __restrict__ partial, int splits, int M, int N, int n_valid, const float* __restrict__ bias, int act,
-            __nv_bfloat16* __restrict__ out_bf16, int ld_out, float* __restrict__ out_f32)
+            __half* __restrict__ out_f16, int ld_out, float* __restrict__ out_f32)
 {
     const int nq = N / 4;
     const size_t total = (size_t)M * nq;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(idx / nq), n = (int)(idx % nq) * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < splits; s++) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)s * M + m) * N + n));
+        const float4* pp = reinterpret_cast<const float4*>(partial + (size_t)m * N + n);
+        const size_t sstride = (size_t)M * N / 4;
+        int s = 0;
+        for (; s + 4 <= splits; s += 4) {                 // four loads in flight, summed in split order
+            const float4 v0 = __ldg(pp + (size_t)s * sstride), v1 = __ldg(pp + (size_t)(s + 1) * sstride);
+            const float4 v2 = __ldg(pp + (size_t)(s + 2) * sstride), v3 = __ldg(pp + (size_t)(s + 3) * sstride);
+            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+            acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+            acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+            acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+        }
+        for (; s < splits; s++) {
+            const float4 v = __ldg(pp + (size_t)s * sstride);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         float o[4] = {acc.x, acc.y, acc.z, acc.w};
@@ -147,10 +165,10 @@ k_fc_finish(const float* __restrict__ partial, int splits, int M, int N, int n_v
             else if (act == 2) v = tanhf(v);
             o[j] = v;
         }
-        if (out_bf16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+        if (out_f16) {
+            __half2 lo = __floats2half2_rn(sat_f16(o[0]), sat_f16(o[1])), hi = __floats2half2_rn(sat_f16(o[2]), sat_f16(o[3]));
             uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-            if (n < ld_out) *reinterpret_cast<uint2*>(out_bf16 + (size_t)m * ld_out + n) = pk;
+            if (n < ld_out) *reinterpret_cast<uint2*>(out_f16 + (size_t)m * ld_out + n) = pk;
         }
         if (out_f32) {
 #pragma unroll
@@ -210,7 +228,7 @@ __device__ __forceinline__ void bin_max8(const __nv_bfloat16* __restrict__ f, in
 __global__ void __launch_bounds__(256)
 k_roi_pool_pair(const __nv_bfloat16* __restrict__ f5, int H5, int W5, const __nv_bfloat16* __restrict__ f4, int H4, int W4,
                 int C, int B, int batch_offset, const float* __restrict__ rois, int roi_stride, int PH, int PW, float scale5,
-                float scale4, __nv_bfloat16* __restrict__ out)
+                float scale4, __half* __restrict__ out)
 {
     extern __shared__ float sred[];   // [kRpSlices - 1][groups][16]
     const int n = blockIdx.x, ph = blockIdx.y / PW, pw = blockIdx.y % PW;
@@ -242,12 +260,12 @@ k_roi_pool_pair(const __nv_bfloat16* __restrict__ f5, int H5, int W5, const __nv
             for (int j = 0; j < 16; j++) m[j] = fmaxf(m[j], q[j]);
         }
         const bool e5 = b5.he <= b5.hs || b5.we <= b5.ws, e4 = b4.he <= b4.hs || b4.we <= b4.ws;   // empty bin -> 0 (.cu.cc:64-65)
-        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+        __half2* po = reinterpret_cast<__half2*>(&o);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float a0 = e5 ? 0.f : m[2 * j], a1 = e5 ? 0.f : m[2 * j + 1];
             const float c0v = e4 ? 0.f : m[8 + 2 * j], c1v = e4 ? 0.f : m[8 + 2 * j + 1];
-            po[j] = __floats2bfloat162_rn(a0 + c0v, a1 + c1v);
+            po[j] = __floats2half2_rn(sat_f16(a0 + c0v), sat_f16(a1 + c1v));
         }
     }
     *reinterpret_cast<uint4*>(out + ((size_t)n * PH * PW + (size_t)ph * PW + pw) * C + c0) = o;
@@ -266,6 +284,7 @@ static void fc_plan(int M, int N, int K, int* splits, int* chunks_per_split)
     int want = kNumSMs / (ntiles * mtiles);
     if (want < 1) want = 1;
     if (want > kchunks) want = kchunks;
+    if (want > 16) want = 16;              // beyond 16 splits the fixed-order reduction costs more than the streaming gains (fc8)
     int cps = (kchunks + want - 1) / want;
     *chunks_per_split = cps;
     *splits = (kchunks + cps - 1) / cps;
@@ -281,25 +300,25 @@ extern "C" int pcnn_fc_workspace_bytes(int M, int N, int K, size_t* bytes)
     return PCNN_OK;
 }
 
-// out = act(A[M,K] @ W[N,K]^T + bias): A, W bf16 row-major (K contiguous); bias [n_valid] f32; act 0 none / 1 ReLU / 2 tanh;
-// out_bf16 [M, ld_out] (optional) and / or out_f32 [M, n_valid] (optional).  Columns n_valid..N of W are padding (zero rows).
-extern "C" int pcnn_fc_bf16_tc(const void* a_bf16, const void* w_bf16, const float* bias, int M, int N, int K, int n_valid,
-                               int act, void* out_bf16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes,
+// out = act(A[M,K] @ W[N,K]^T + bias): A, W fp16 row-major (K contiguous); bias [n_valid] f32; act 0 none / 1 ReLU / 2 tanh;
+// out_f16 [M, ld_out] (optional) and / or out_f32 [M, n_valid] (optional).  Columns n_valid..N of W are padding (zero rows).
+extern "C" int pcnn_fc_f16_tc(const void* a_f16, const void* w_f16, const float* bias, int M, int N, int K, int n_valid,
+                              int act, void* out_f16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes,
                                void* stream)
 {
-    PCNN_REQUIRE(a_bf16 && w_bf16 && bias && workspace && (out_bf16 || out_f32), "fc: NULL tensor pointer");
+    PCNN_REQUIRE(a_f16 && w_f16 && bias && workspace && (out_f16 || out_f32), "fc: NULL tensor pointer");
     size_t need = 0;
     int rc = pcnn_fc_workspace_bytes(M, N, K, &need);
     if (rc) return rc;
     PCNN_REQUIRE(n_valid >= 1 && n_valid <= N && act >= 0 && act <= 2, "fc: bad n_valid / act (%d, %d)", n_valid, act);
-    PCNN_REQUIRE(!out_bf16 || (ld_out % 4 == 0 && ld_out >= 4), "fc: ld_out must be a multiple of 4 (got %d)", ld_out);
+    PCNN_REQUIRE(!out_f16 || (ld_out % 4 == 0 && ld_out >= 4), "fc: ld_out must be a multiple of 4 (got %d)", ld_out);
     if (workspace_bytes < need) { set_error("fc: workspace too small (%zu < %zu)", workspace_bytes, need); return PCNN_E_WORKSPACE; }
     int splits, cps;
     fc_plan(M, N, K, &splits, &cps);
     CUtensorMap ma, mw;
-    rc = make_map_weights(&ma, a_bf16, K, M, kTileM);
+    rc = make_map_weights(&ma, a_f16, K, M, kTileM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     if (rc) return rc;
-    rc = make_map_weights(&mw, w_bf16, K, N, kFcBN);
+    rc = make_map_weights(&mw, w_f16, K, N, kFcBN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     if (rc) return rc;
     PCNN_SMEM_OPTIN(k_fc_tc, kFcSmem, "fc_tc");
     cudaStream_t st = (cudaStream_t)stream;
@@ -310,18 +329,18 @@ extern "C" int pcnn_fc_bf16_tc(const void* a_bf16, const void* w_bf16, const flo
     const size_t total = (size_t)M * (N / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    k_fc_finish<<<blocks, 256, 0, st>>>((const float*)workspace, splits, M, N, n_valid, bias, act, (__nv_bfloat16*)out_bf16, ld_out,
+    k_fc_finish<<<blocks, 256, 0, st>>>((const float*)workspace, splits, M, N, n_valid, bias, act, (__half*)out_f16, ld_out,
                                         out_f32);
     return check_launch("fc_finish");
 }
 
 // pool_score = RoiPool(conv5_3, 1/16) + RoiPool(conv4_3, 1/8) (vgg16_convs.py:177-183) flattened to the fc6 operand:
-// f5 [B,H5,W5,C] bf16, f4 [B,H4,W4,C] bf16, rois [N, roi_stride] (batch index = rois[:,0] - batch_offset) -> out [N, PH*PW*C] bf16
-extern "C" int pcnn_roi_pool_pair_bf16(const void* f5, int H5, int W5, const void* f4, int H4, int W4, int C, int B,
+// f5 [B,H5,W5,C] bf16, f4 [B,H4,W4,C] bf16, rois [N, roi_stride] (batch index = rois[:,0] - batch_offset) -> out [N, PH*PW*C] fp16
+extern "C" int pcnn_roi_pool_pair_f16(const void* f5, int H5, int W5, const void* f4, int H4, int W4, int C, int B,
                                        int batch_offset, const float* rois, int num_rois, int roi_stride, int pooled_h,
-                                       int pooled_w, float scale5, float scale4, void* out_bf16, void* stream)
+                                       int pooled_w, float scale5, float scale4, void* out_f16, void* stream)
 {
-    PCNN_REQUIRE(f5 && f4 && rois && out_bf16, "roi_pool_pair: NULL tensor pointer");
+    PCNN_REQUIRE(f5 && f4 && rois && out_f16, "roi_pool_pair: NULL tensor pointer");
     PCNN_REQUIRE(C % 8 == 0 && C >= 8 && num_rois >= 1 && roi_stride >= 6 && pooled_h >= 1 && pooled_w >= 1 && B >= 1,
                  "roi_pool_pair: bad shape (C = %d, rois = %d x %d)", C, num_rois, roi_stride);
     PCNN_REQUIRE(pooled_h * pooled_w <= 65535 && C / 8 * kRpSlices <= 256 && 256 % (C / 8) == 0,
@@ -331,6 +350,6 @@ extern "C" int pcnn_roi_pool_pair_bf16(const void* f5, int H5, int W5, const voi
     const size_t smem = sizeof(float) * (size_t)(kRpSlices - 1) * (C / 8) * 16;
     k_roi_pool_pair<<<grid, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)f5, H5, W5, (const __nv_bfloat16*)f4, H4, W4,
                                                                  C, B, batch_offset, rois, roi_stride, pooled_h, pooled_w, scale5,
-                                                                 scale4, (__nv_bfloat16*)out_bf16);
+                                                                 scale4, (__half*)out_f16);
     return check_launch("roi_pool_pair");
 }

@@ -339,6 +339,77 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_up8_label: label-only form of k_up8_heads for the pipeline (Hough samples its vertex values from `lowres`): one CTA per
+// (low-resolution row, image) produces the EIGHT output rows that row owns.  The three contributing low-resolution rows'
+// score channels are staged once (k_up8_heads re-stages two rows for every output row); per output row, thread =
+// (cell, class pair) blends vertically in registers, emits the cell's 8 pixels into a shared score row, and thread =
+// pixel takes the arg-max (lowest index on ties).  Same operation sequence as k_up8_heads (heads_common.cuh): identical
+// labels.  CT = compile-time class count (even).
+// ---------------------------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(256)
+k_up8_label(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/, int h, int w, int C_rt,
+            int* __restrict__ label /*[B,8h,8w]*/)
+{
+    extern __shared__ float smem_f[];
+    const int C = CT ? CT : C_rt;
+    const int No = 4 * C, C2 = C / 2, W = 8 * w;
+    float2* rows = reinterpret_cast<float2*>(smem_f);              // [3][w][C2]: low-resolution rows my - 1, my, my + 1 (score channels)
+    float* sc = smem_f + (size_t)3 * w * C;                        // [W][C] scores of one output row
+    const int my = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+    for (int i = t; i < 3 * w * C2; i += 256) {
+        const int r = i / (w * C2), j = i - r * (w * C2);
+        const int cell = j / C2, c2 = j - cell * C2;
+        const int iy = min(max(my - 1 + r, 0), h - 1);             // clamped like k_up8_heads; out-of-range rows get weight 0
+        rows[i] = __ldg(reinterpret_cast<const float2*>(lr + (((size_t)n * h + iy) * w + cell) * No) + c2);
+    }
+    __syncthreads();
+    const float2 zero = make_float2(0.f, 0.f);
+    for (int ty = 0; ty < 8; ty++) {
+        const int y = 8 * my + ty;
+        const int iy0 = ty < 4 ? my - 1 : my, iy1 = iy0 + 1;
+        const float wy0 = (iy0 >= 0 && iy0 < h) ? deconv_w(y - 8 * iy0 + 4, 16) : 0.f;
+        const float wy1 = (iy1 >= 0 && iy1 < h) ? deconv_w(y - 8 * iy1 + 4, 16) : 0.f;
+        const float2* r0 = rows + (size_t)(iy0 - (my - 1)) * w * C2;     // staged slot of row iy0 (slot 0..2); clamping is
+        const float2* r1 = rows + (size_t)(iy1 - (my - 1)) * w * C2;     // irrelevant where the weight is 0, identical otherwise
+        for (int i = t; i < w * C2; i += 256) {
+            const int mx = i / C2, c2 = i - mx * C2;
+            const float2 bb = make_float2(__ldg(bias_s + 2 * c2), __ldg(bias_s + 2 * c2 + 1));
+            auto vb = [&](int cell) -> float2 {
+                const float2 a = r0[cell * C2 + c2], b = r1[cell * C2 + c2];
+                return make_float2(up8_vblend(wy0, a.x, wy1, b.x), up8_vblend(wy0, a.y, wy1, b.y));
+            };
+            const float2 vl = mx > 0 ? vb(mx - 1) : zero;
+            const float2 vc = vb(mx);
+            const float2 vr = mx + 1 < w ? vb(mx + 1) : zero;
+            float* sp = sc + (size_t)8 * mx * C + 2 * c2;
+#pragma unroll
+            for (int tx = 0; tx < 8; tx++) {
+                const float wa = deconv_w(tx < 4 ? tx + 12 : tx + 4, 16), wb = deconv_w(tx < 4 ? tx + 4 : tx - 4, 16);
+                const float2 a = tx < 4 ? vl : vc, b = tx < 4 ? vc : vr;
+                const float v0 = fmaxf(up8_hblend(wa, a.x, wb, b.x, bb.x), 0.f);      // `score` has a ReLU
+                const float v1 = fmaxf(up8_hblend(wa, a.y, wb, b.y, bb.y), 0.f);
+                *reinterpret_cast<float2*>(sp + tx * C) = make_float2(v0, v1);
+            }
+        }
+        __syncthreads();
+        for (int x = t; x < W; x += 256) {
+            const float2* s2 = reinterpret_cast<const float2*>(sc + (size_t)x * C);
+            float best = s2[0].x;
+            int bi = 0;
+            if (s2[0].y > best) { best = s2[0].y; bi = 1; }
+            for (int c = 1; c < C2; c++) {
+                const float2 v = s2[c];
+                if (v.x > best) { best = v.x; bi = 2 * c; }
+                if (v.y > best) { best = v.y; bi = 2 * c + 1; }
+            }
+            label[((size_t)n * 8 * h + y) * W + x] = bi;
+        }
+        __syncthreads();
+    }
+}
+
 // generic bilinear transposed convolution (depthwise, diagonal filter): out[B,s*h,s*w,C] f32 from in[B,h,w,C] f32.
 // Only used by tests / the un-fused reference path.
 __global__ void __launch_bounds__(256)
@@ -402,6 +473,21 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
     PCNN_REQUIRE(C >= 1 && B >= 1 && h >= 1 && w >= 1, "up8_heads: bad shape");
     PCNN_REQUIRE(8 * h <= 65535 * 1 && B <= 65535, "up8_heads: image too tall for the launch grid");
     PCNN_REQUIRE(C % 2 == 0 && 2 * C <= 256, "up8_heads: num_classes must be even and <= 128 (got %d)", C);
+    if (!vertex && !prob && !score) {
+        // label-only fast path: one CTA per low-resolution row (8 output rows), three staged rows + one score row in smem
+        const size_t smem_l = sizeof(float) * ((size_t)3 * w * C + (size_t)8 * w * C);
+        if (smem_l <= 200 * 1024 && h <= 65535) {
+            dim3 grid_l(h, B);
+            if (C == 22) {
+                PCNN_SMEM_OPTIN(k_up8_label<22>, 200 * 1024, "up8_label<22>");
+                k_up8_label<22><<<grid_l, 256, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
+            } else {
+                PCNN_SMEM_OPTIN(k_up8_label<0>, 200 * 1024, "up8_label<0>");
+                k_up8_label<0><<<grid_l, 256, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
+            }
+            return check_launch("up8_label");
+        }
+    }
     int seg_cells = w <= 20 ? w : 20;  // 160 output pixels per CTA
     size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: segment does not fit shared memory (C = %d)", C);

@@ -81,8 +81,12 @@ k_nms_pose(const float* __restrict__ rois /*[cap,7]*/, const float* __restrict__
             const int gj = box[j].img;
             gr += (gj < gi) || (gj == gi && bef);
         }
-        rank[i] = r;
+        // output position key: processing order inside the row's group; with per_image the groups (images) come in
+        // ascending order, like the reference op loops the batch (hough_voting_gpu_op.cc:369-377) — so the rows of
+        // image shards, concatenated in rank order, are the rows of the whole batch
+        rank[i] = gr;
         grouped[gr] = i;
+        (void)r;
     }
     __syncthreads();
     // group boundaries in the grouped order
@@ -110,7 +114,7 @@ k_nms_pose(const float* __restrict__ rois /*[cap,7]*/, const float* __restrict__
         }
     }
     __syncthreads();
-    // compaction in processing order + pose assembly (test.py:204-211)
+    // compaction in (image, processing order) + pose assembly (test.py:204-211); one group = plain processing order
     for (int i = t; i < N; i += kNmsThreads) {
         if (dead[i]) continue;
         const int ri = rank[i];

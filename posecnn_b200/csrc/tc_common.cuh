@@ -147,6 +147,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     return d;
 }
 
+// same with FP16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int bn)
+{
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
 __host__ __device__ constexpr uint32_t make_idesc(int bn)
 {
     // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, K-major A and B, N>>3 @17, M>>4 @24
@@ -170,7 +176,8 @@ static inline EncodeTiledFn get_encode()
     return fn;
 }
 
-static inline int make_map_weights(CUtensorMap* m, const void* ptr, int K, int Cout, int bn)
+static inline int make_map_weights(CUtensorMap* m, const void* ptr, int K, int Cout, int bn,
+                                   CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return PCNN_E_CUDA; }
@@ -178,7 +185,7 @@ static inline int make_map_weights(CUtensorMap* m, const void* ptr, int K, int C
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {kKC, (cuuint32_t)bn};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(m, dtype, 2, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%d) failed: %d", Cout, K, (int)r); return PCNN_E_CUDA; }

@@ -152,7 +152,7 @@ class vgg16_convs:
             else:
                 T[name] = conv.hwio_to_tc(w)
         for name in ("fc6", "fc7", "fc8"):
-            T[f"{name}/weights"] = pose_head.fc_weights_to_tc(P[f"{name}/weights"])   # [out (padded to x128), in] bf16
+            T[f"{name}/weights"] = pose_head.fc_weights_to_tc(P[f"{name}/weights"])   # [out (padded to x128), in] fp16
         T["score/w"] = P["score/weights"].reshape(self.num_units, self.num_classes).contiguous()
         T["vertex_pred/w"] = P["vertex_pred/weights"].reshape(128, 3 * self.num_classes).contiguous()
         if self.fold_vertex_head:
@@ -272,7 +272,7 @@ class vgg16_convs:
                 p5, a5 = roi_pooling_op.roi_pool(c5, rl, 7, 7, 1.0 / 16.0, 0)
                 p4, a4 = roi_pooling_op.roi_pool(c4, rl, 7, 7, 1.0 / 8.0, 0)
                 L["pool5_argmax"], L["pool4_argmax"] = a5, a4
-                x = (p5 + p4).reshape(cap_rows, -1).to(torch.bfloat16)                 # pool_score, flatten (h, w, c)
+                x = (p5 + p4).reshape(cap_rows, -1).clamp(-65504.0, 65504.0).to(torch.float16)   # pool_score, flatten (h, w, c)
             else:
                 x = pose_head.roi_pool_pair(c5, c4, rois, 7, 7, 1.0 / 16.0, 1.0 / 8.0, batch_offset)
             L["pool_score"] = x

@@ -25,7 +25,7 @@ def _rois(n, B, W, H, seed):
 
 
 def test_roi_pool_pair_equals_two_roi_pools(cuda):
-    """k_roi_pool_pair == bf16(RoiPool(conv5_3, 1/16) + RoiPool(conv4_3, 1/8)) of the parity-tested RoiPool op: exact."""
+    """k_roi_pool_pair == fp16(RoiPool(conv5_3, 1/16) + RoiPool(conv4_3, 1/8)) of the parity-tested RoiPool op: exact."""
     from posecnn_b200 import pose_head
     from posecnn_b200.roi_pooling_layer import roi_pooling_op as rop
     g = torch.Generator().manual_seed(0)
@@ -36,7 +36,7 @@ def test_roi_pool_pair_equals_two_roi_pools(cuda):
     got = pose_head.roi_pool_pair(f5, f4, rois)
     p5, _ = rop.roi_pool(f5, rois, 7, 7, 1.0 / 16.0, 0)
     p4, _ = rop.roi_pool(f4, rois, 7, 7, 1.0 / 8.0, 0)
-    want = (p5 + p4).reshape(rois.shape[0], -1).to(torch.bfloat16)
+    want = (p5 + p4).reshape(rois.shape[0], -1).to(torch.float16)
     assert torch.equal(got, want)
     # image shard: global batch indices shifted by batch_offset select the same local images; foreign rows pool zeros
     shifted = rois.clone(); shifted[:, 0] += 5
@@ -48,23 +48,23 @@ def test_roi_pool_pair_equals_two_roi_pools(cuda):
 @pytest.mark.parametrize("M,K,N,act", [(128, 25088, 4096, "relu"), (128, 4096, 4096, "relu"), (128, 4096, 88, "tanh"),
                                         (37, 1024, 256, "none"), (300, 512, 128, "relu")])
 def test_fc_tc_against_fp32_matmul(cuda, M, K, N, act):
-    """Split-K tcgen05 GEMM + fused epilogue against an fp64 product of the SAME bf16-rounded operands (isolates the
-    kernel from the operand rounding): |err| <= 1e-3 * (1 + |ref|) before the bf16 output rounding, bf16-exact after."""
+    """Split-K tcgen05 GEMM + fused epilogue against an fp64 product of the SAME fp16-rounded operands (isolates the
+    kernel from the operand rounding): |err| <= 1e-3 * (1 + |ref|) before the fp16 output rounding, fp16-exact after."""
     from posecnn_b200 import pose_head
     g = torch.Generator().manual_seed(K + N)
-    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(torch.float16)
     w = (torch.randn(K, N, generator=g) / np.sqrt(K)).float()
     bias = torch.randn(N, generator=g) * 0.1
     w_tc = pose_head.fc_weights_to_tc(w.to(cuda))
     assert w_tc.shape == ((N + 127) // 128 * 128, K)
-    ref = a.double() @ w.to(torch.bfloat16).double() + bias.double()
+    ref = a.double() @ w.to(torch.float16).double() + bias.double()
     ref = {"relu": torch.relu, "tanh": torch.tanh, "none": lambda t: t}[act](ref)
     out32 = pose_head.fc(a.to(cuda), w_tc, bias.to(cuda), act, torch.float32).cpu().double()
     assert out32.shape == (M, N)
     assert torch.all((out32 - ref).abs() <= 1e-3 * (1 + ref.abs())), float((out32 - ref).abs().max())
-    out16 = pose_head.fc(a.to(cuda), w_tc, bias.to(cuda), act, torch.bfloat16).cpu()
+    out16 = pose_head.fc(a.to(cuda), w_tc, bias.to(cuda), act, torch.float16).cpu()
     assert out16.shape == (M, w_tc.shape[0])
-    assert torch.equal(out16[:, :N], out32.float().to(torch.bfloat16))          # same accumulation, one rounding
+    assert torch.equal(out16[:, :N], out32.float().to(torch.float16))          # same accumulation, one rounding
     assert float(out16[:, N:].float().abs().max()) == 0.0 if w_tc.shape[0] > N else True
     again = pose_head.fc(a.to(cuda), w_tc, bias.to(cuda), act, torch.float32).cpu().double()
     assert torch.equal(again, out32)                                            # fixed-order split-K reduction

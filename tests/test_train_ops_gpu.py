@@ -178,7 +178,7 @@ def test_vertex_loss_fused_equals_materialised(cuda):
 def test_multi_instance_vertex_targets_match_reference_golden(cuda):
     """pcnn_vertex_targets_instances_fwd vs the reference function's own output on the multi-instance branch
     (minibatch.py:549-573; tests/golden/vertex_targets_multi.npz): direction components bit-exact, log z to 1 ulp of libm."""
-    from tests.golden import cases
+    from posecnn_b200 import train_ops
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vertex_targets_multi.npz"))
     label, mask, inst = cases.vertex_target_multi_inputs()
     t, w = train_ops.generate_vertex_targets_instances(T(label, cuda), T(mask, cuda), T(inst, cuda), 6, 10.0)
@@ -193,7 +193,7 @@ def test_pack_pose_meta_matches_data_layer_restatement(cuda):
     """pcnn_pack_pose_meta_fwd vs oracle.pack_pose_meta (minibatch.py:440-451, 474-492): row order / class / image columns
     exact, quaternions (Jacobi vs LAPACK eigh) and translations 1e-6, meta_data 1e-6 relative (cofactor inverse vs pinv)."""
     from scipy.spatial.transform import Rotation
-    from posecnn_b200 import synth
+    from posecnn_b200 import synth, train_ops
     rng = np.random.default_rng(9)
     B, I = 3, 5
     poses = np.zeros((B, I, 3, 4), np.float32)

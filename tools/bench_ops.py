@@ -68,9 +68,9 @@ ms = timeit(lambda: pose_head.roi_pool_pair(f5, f4, rois)); report("roi_pool_pai
 xa = pose_head.roi_pool_pair(f5, f4, rois)
 for nm, K, N in (("fc6", 25088, 4096), ("fc7", 4096, 4096), ("fc8", 4096, 88)):
     wt = pose_head.fc_weights_to_tc(torch.randn((K, N), device=dev) * 0.01); bs = torch.zeros(N, device=dev)
-    a = xa if K == 25088 else torch.randn((128, K), device=dev).to(torch.bfloat16)
-    ms = timeit(lambda: pose_head.fc(a, wt, bs, "relu" if N > 88 else "tanh", torch.bfloat16 if N > 88 else torch.float32))
-    report(f"{nm} 128 x {K} x {N} bf16 (split-K tcgen05 + finish)", ms, wt.numel() * 2 + 128 * K * 2 + 128 * N * 4, "weights + A + out; 2*M*K*N = %.1f GFLOP" % (2 * 128 * K * N / 1e9))
+    a = xa if K == 25088 else torch.randn((128, K), device=dev).to(torch.float16)
+    ms = timeit(lambda: pose_head.fc(a, wt, bs, "relu" if N > 88 else "tanh", torch.float16 if N > 88 else torch.float32))
+    report(f"{nm} 128 x {K} x {N} fp16 (split-K tcgen05 + finish)", ms, wt.numel() * 2 + 128 * K * 2 + 128 * N * 4, "weights + A + out; 2*M*K*N = %.1f GFLOP" % (2 * 128 * K * N / 1e9))
     del wt
 del f5, f4, xa
 # Project / Backproject, G = 128, Cf = 64, batch 4 (8.6 GB of voxel grids at batch 4)
