@@ -209,12 +209,50 @@ int pcnn_conv_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int 
 int pcnn_conv_wgrad_bf16_tc(const void* x_bf16, const void* dz_bf16, int B, int H, int W, int Cin, int Cout, int ksize,
                             float scale, const float* w_f32, float decay, float* dW, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* fully connected layer: x [rows, Cin], dy [rows, Cout] fp16 -> dW [Cout][Cin] f32; workspace: pcnn_conv_wgrad_workspace_bytes(1, 1, rows, Cin, Cout, 1) */
+int pcnn_fc_wgrad_f16_tc(const void* x_f16, const void* dy_f16, int rows, int Cin, int Cout, float scale, const float* w_f32,
+                         float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream);
 int pcnn_bias_ws_bytes(int C, size_t* bytes);
 int pcnn_relu_bwd_bf16(const void* g_bf16, const void* y_bf16, size_t npix, int C, int has_relu, void* dz_bf16, float scale,
                        const float* b, float decay, float* db, void* bias_ws, size_t bias_ws_bytes, void* stream);
 int pcnn_maxpool_relu_bwd_bf16(const void* g_bf16, const void* y_bf16, int B, int H, int W, int C, void* dz_bf16, float scale,
                                const float* b, float decay, float* db, void* bias_ws, size_t bias_ws_bytes, void* stream);
 int pcnn_add_to_bf16(const void* a_bf16, const void* b_bf16, const float* b_f32, size_t n, void* out_bf16, void* stream);
+
+/* Small kernels of the training step around those GEMMs (csrc/train_bwd.cu); training graph lib/networks/vgg16_convs.py:128-212,
+ * losses lib/fcn/train.py:455-465, 564-573, optimizer tf.train.MomentumOptimizer (train.py:633):
+ *  pcnn_add_up2_bf16 / pcnn_up2_bwd_bf16   add = a4 + up2(a5) (fixed bilinear conv2d_transpose 4x4 / 2) and its adjoint (+ ReLU mask of a5)
+ *  pcnn_pack_lowres       [score C | vertex 3C] f32 head tensor from the two bf16 1x1-convolution outputs (row strides Cs, Cv)
+ *  pcnn_up8_heads_bwd     gradient of loss_cls (Hardlabel-selected cross entropy through log-softmax and the ReLU of `score`) and of
+ *                         loss_vertex (smooth L1 on the labelled pixels' own class) w.r.t. the low-resolution head tensor, formed from
+ *                         the loss structure on the fly: d_sc [B,h,w,Cs], d_vt [B,h,w,Cv] bf16 (padding channels zero), dbias [4C]
+ *  pcnn_pose_chain_bwd    Averagedistance's bottom_diff through l2_normalize, * poses_weight and tanh -> d fc8 pre-activation (fp16)
+ *  pcnn_sgd_momentum      accum = mu * accum + (gscale * grad + wd * w); w -= lr * accum; refreshed 16-bit tensor-core copy (kind 0 bf16, 1 fp16)
+ *  pcnn_transpose16 / pcnn_half_to_float   layout / precision glue of the fully connected backward GEMMs
+ *  pcnn_conv1_wgrad       conv1_1 weight gradient (Cin = 3) on the CUDA cores, input = uint8 image - mean
+ */
+int pcnn_add_up2_bf16(const void* a4_bf16, const void* a5_bf16, int B, int h, int w, int C, void* out_bf16, void* stream);
+int pcnn_up2_bwd_bf16(const void* dadd_bf16, const void* y5_bf16, int B, int h, int w, int C, void* d5_bf16, void* stream);
+int pcnn_pack_lowres(const void* sc_bf16, int Cs, const void* vt_bf16, int Cv, int B, int h, int w, int C, float* lowres, void* stream);
+int pcnn_up8_heads_bwd(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
+                       float threshold, const float* vertex_pred, const float* centers, const float* vertex_loss_out,
+                       float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C, int Cs, int Cv,
+                       void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+int pcnn_pose_chain_bwd(const float* bottom_diff, const float* poses_tanh, const float* poses_weight, int N, int D, float upstream,
+                        void* dpre_f16, int ld, void* stream);
+int pcnn_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float lr, float mu, float wd, float gscale, void* copy16,
+                      int kind, void* stream);
+/* loss_cross_entropy_single_frame on the Hardlabel selection from the RAW `score` layer (log-softmax per selected pixel) */
+int pcnn_loss_cls_hard_raw_fwd(const float* score_raw, const float* prob, const int32_t* gt, int B, int H, int W, int C,
+                               float threshold, float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+/* input gradient of a fully connected layer: out [M, ld_out] fp16 = (dy [M,K] @ W[N,K]^T) * [relu_mask > 0]; W = the layer's weights in
+ * TF layout [in = N][out = K] fp16 (K contiguous); relu_mask [M, ld_out] fp16 = stored output of the ReLU layer below, or NULL */
+int pcnn_fc_dgrad_f16_tc(const void* dy_f16, const void* w_in_out_f16, int M, int N, int K, const void* relu_mask_f16, void* out_f16,
+                         int ld_out, void* workspace, size_t workspace_bytes, void* stream);
+int pcnn_transpose16(const void* in, int rows, int cols, void* out, void* stream);
+int pcnn_half_to_float(const void* src_f16, size_t n, float* dst, void* stream);
+int pcnn_conv1_wgrad(const void* img_u8, const float* mean3_host, const void* dz_bf16, int B, int H, int W, float scale,
+                     const float* w, float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Pose-regression head (networks/vgg16_convs.py:177-197, Network.fc networks/network.py:392-422, tanh :436-438) on own

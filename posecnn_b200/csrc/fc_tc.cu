@@ -134,7 +134,7 @@ __device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504
 // out_f16 (row stride ld_out, the next layer's A operand) and / or out_f32 (row stride n_valid).
 __global__ void __launch_bounds__(256)
 k_fc_finish(const float* __restrict__ partial, int splits, int M, int N, int n_valid, const float* __restrict__ bias, int act,
-            __half* __restrict__ out_f16, int ld_out, float* __restrict__ out_f32)
+            __half* __restrict__ out_f16, int ld_out, float* __restrict__ out_f32, const __half* __restrict__ relu_mask /*[M, ld_out] or null*/)
 {
     const int nq = N / 4;
     const size_t total = (size_t)M * nq;
@@ -160,9 +160,10 @@ k_fc_finish(const float* __restrict__ partial, int splits, int M, int N, int n_v
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (n + j >= n_valid) { o[j] = 0.f; continue; }
-            float v = o[j] + __ldg(bias + n + j);
+            float v = o[j] + (bias ? __ldg(bias + n + j) : 0.f);
             if (act == 1) v = fmaxf(v, 0.f);
             else if (act == 2) v = tanhf(v);
+            if (relu_mask && !(__half2float(relu_mask[(size_t)m * ld_out + n + j]) > 0.f)) v = 0.f;   // backward through a ReLU layer
             o[j] = v;
         }
         if (out_f16) {
@@ -302,11 +303,28 @@ extern "C" int pcnn_fc_workspace_bytes(int M, int N, int K, size_t* bytes)
 
 // out = act(A[M,K] @ W[N,K]^T + bias): A, W fp16 row-major (K contiguous); bias [n_valid] f32; act 0 none / 1 ReLU / 2 tanh;
 // out_f16 [M, ld_out] (optional) and / or out_f32 [M, n_valid] (optional).  Columns n_valid..N of W are padding (zero rows).
+static int fc_impl(const void* a_f16, const void* w_f16, const float* bias, int M, int N, int K, int n_valid, int act, void* out_f16,
+                   int ld_out, float* out_f32, const void* relu_mask_f16, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int pcnn_fc_f16_tc(const void* a_f16, const void* w_f16, const float* bias, int M, int N, int K, int n_valid,
                               int act, void* out_f16, int ld_out, float* out_f32, void* workspace, size_t workspace_bytes,
                                void* stream)
 {
-    PCNN_REQUIRE(a_f16 && w_f16 && bias && workspace && (out_f16 || out_f32), "fc: NULL tensor pointer");
+    return fc_impl(a_f16, w_f16, bias, M, N, K, n_valid, act, out_f16, ld_out, out_f32, nullptr, workspace, workspace_bytes, stream);
+}
+
+// input-gradient GEMM of a fully connected layer: out = (A @ W^T)[m][n] * [relu_mask[m][n] > 0] (mask = the stored output of the
+// ReLU layer below, [M, ld_out] fp16; NULL = no mask), bias NULL allowed
+extern "C" int pcnn_fc_dgrad_f16_tc(const void* dy_f16, const void* w_in_out_f16, int M, int N, int K, const void* relu_mask_f16,
+                                    void* out_f16, int ld_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return fc_impl(dy_f16, w_in_out_f16, nullptr, M, N, K, N, 0, out_f16, ld_out, nullptr, relu_mask_f16, workspace, workspace_bytes, stream);
+}
+
+static int fc_impl(const void* a_f16, const void* w_f16, const float* bias, int M, int N, int K, int n_valid, int act, void* out_f16,
+                   int ld_out, float* out_f32, const void* relu_mask_f16, void* workspace, size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(a_f16 && w_f16 && workspace && (out_f16 || out_f32), "fc: NULL tensor pointer");
     size_t need = 0;
     int rc = pcnn_fc_workspace_bytes(M, N, K, &need);
     if (rc) return rc;
@@ -330,7 +348,7 @@ extern "C" int pcnn_fc_f16_tc(const void* a_f16, const void* w_f16, const float*
     int blocks = (int)((total + 255) / 256);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
     k_fc_finish<<<blocks, 256, 0, st>>>((const float*)workspace, splits, M, N, n_valid, bias, act, (__half*)out_f16, ld_out,
-                                        out_f32);
+                                        out_f32, (const __half*)relu_mask_f16);
     return check_launch("fc_finish");
 }
 

@@ -1,0 +1,425 @@
+// train_bwd.cu — the small kernels of the training step around the tensor-core GEMMs (csrc/wgrad_tc.cu, conv_tc.cu,
+// fc_tc.cu): the un-fused FCN heads of the training graph and their gradients, the pose-loss chain, SGD with momentum.
+//
+// Training graph (lib/networks/vgg16_convs.py:128-212, lib/fcn/train.py:486-500), heads part:
+//   add_score        = score_conv4 + up2(score_conv5)                  (deconv 4x4 / 2, fixed bilinear filter)
+//   upscore -> score = relu(conv1x1(up8(add_score)) + b)  ==  relu(up8(conv1x1_nobias(add_score)) + b)   (commuted, heads.cu)
+//   loss_cls         = -sum_{selected p} log_softmax(score)[p, gt_p] / count     (Hardlabel selection, train.py:455-465)
+//   vertex_pred likewise from add_score_vertex; loss_vertex = smooth-L1 on the labelled pixels' own class (train.py:564-573)
+// Backward pieces here:
+//   k_up8_bwd       d lowres[b, my, mx, ch] = sum_{y, x} Wy Wx d up[b, y, x, ch]  with d up formed on the fly from the loss
+//                   structure (one-hot cross-entropy through log-softmax and ReLU; sparse smooth-L1), never materialised
+//   k_add_up2 / k_up2_bwd   add = a4 + up2(a5) and its adjoint (+ ReLU mask)
+//   k_pose_chain_bwd        d fc8 pre-activation from Averagedistance's bottom_diff through l2_normalize, * weight, tanh
+//   k_sgd_momentum          accum = mu * accum + g; w -= lr * accum (tf.train.MomentumOptimizer, train.py:633) + refreshed
+//                           bf16 / fp16 tensor-core copy of the weights
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+
+#include "common.cuh"
+#include "heads_common.cuh"
+
+namespace pcnn {
+
+// ---------------------------------------------------------------------------------------------
+// add[b,h,w,c] = a4[b,h,w,c] + sum_i a5[b, i, j, c] * W4[h - 2 i + 1] * W4[w - 2 j + 1]   (conv2d_transpose 4x4 / 2, SAME)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_add_up2(const __nv_bfloat16* __restrict__ a4, const __nv_bfloat16* __restrict__ a5, int B, int h, int w, int C,
+          __nv_bfloat16* __restrict__ out)
+{
+    const int h5 = h / 2, w5 = w / 2;
+    const size_t total = (size_t)B * h * w * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int x = (int)(r % w); r /= w;
+        const int y = (int)(r % h);
+        const size_t n = r / h;
+        float acc = __bfloat162float(a4[i]);
+        // contributing source rows: ky = y - 2 iy + 1 in [0, 4)
+        for (int iy = (y - 2) / 2; iy <= (y + 1) / 2; iy++) {
+            const int ky = y - 2 * iy + 1;
+            if (iy < 0 || iy >= h5 || ky < 0 || ky >= 4) continue;
+            for (int ix = (x - 2) / 2; ix <= (x + 1) / 2; ix++) {
+                const int kx = x - 2 * ix + 1;
+                if (ix < 0 || ix >= w5 || kx < 0 || kx >= 4) continue;
+                acc = fmaf(deconv_w(ky, 4) * deconv_w(kx, 4), __bfloat162float(a5[((n * h5 + iy) * w5 + ix) * C + c]), acc);
+            }
+        }
+        out[i] = __float2bfloat16_rn(acc);
+    }
+}
+
+// d a5[b, i, j, c] = [y5 > 0 or no relu] * sum_{y, x} W4[y - 2 i + 1] W4[x - 2 j + 1] d add[b, y, x, c]
+__global__ void __launch_bounds__(256)
+k_up2_bwd(const __nv_bfloat16* __restrict__ dadd /*[B,h,w,C]*/, const __nv_bfloat16* __restrict__ y5 /*[B,h/2,w/2,C] or null*/, int B,
+          int h, int w, int C, __nv_bfloat16* __restrict__ d5)
+{
+    const int h5 = h / 2, w5 = w / 2;
+    const size_t total = (size_t)B * h5 * w5 * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int ix = (int)(r % w5); r /= w5;
+        const int iy = (int)(r % h5);
+        const size_t n = r / h5;
+        float acc = 0.f;
+        if (!y5 || __bfloat162float(y5[i]) > 0.f) {
+            for (int ky = 0; ky < 4; ky++) {
+                const int y = 2 * iy - 1 + ky;
+                if (y < 0 || y >= h) continue;
+                for (int kx = 0; kx < 4; kx++) {
+                    const int x = 2 * ix - 1 + kx;
+                    if (x < 0 || x >= w) continue;
+                    acc = fmaf(deconv_w(ky, 4) * deconv_w(kx, 4), __bfloat162float(dadd[((n * h + y) * w + x) * C + c]), acc);
+                }
+            }
+        }
+        d5[i] = __float2bfloat16_rn(acc);
+    }
+}
+
+// lowres [B,h,w,4C] f32 = [score part (first C of sc, row stride Cs) | vertex part (first 3C of vt, row stride Cv)]
+__global__ void __launch_bounds__(256)
+k_pack_lowres(const __nv_bfloat16* __restrict__ sc, int Cs, const __nv_bfloat16* __restrict__ vt, int Cv, size_t npix, int C,
+              float* __restrict__ lowres)
+{
+    const int No = 4 * C;
+    const size_t total = npix * No;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % No);
+        const size_t p = i / No;
+        lowres[i] = ch < C ? __bfloat162float(sc[p * Cs + ch]) : __bfloat162float(vt[p * Cv + ch - C]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_up8_bwd: gradient of both losses w.r.t. the low-resolution head tensor.
+//   score channel c:  d up[p, c] = up_cls * sel_p * (prob[p, c] - [c == gt_p]) / (count + 1e-10) * [score[p, c] > 0]
+//                     sel_p = gt_p != -1 and (gt_p > 0 or prob[p, gt_p] < threshold)          (Hardlabel, constant mask)
+//   vertex channel 3c+k: pixels labelled c with a listed centre: up_vtx * w_inside * smoothL1'(w_inside (pred - target)) / (sum w + 1e-10)
+// One CTA per (low-resolution row, image); thread = (cell, channel), channel fastest (coalesced prob / score reads).
+// Outputs d lowres as TWO bf16 tensors in the layouts the 1x1 backward GEMMs read: d_sc [B,h,w,Cs] (first C channels,
+// rest zero) and d_vt [B,h,w,Cv] (first 3C channels), plus per-CTA partial sums of d bias (the up-sampling weights of a
+// pixel sum to the same value for bias: d b[ch] = sum_p d up[p, ch]).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_up8_bwd(const float* __restrict__ prob, const float* __restrict__ score, const int* __restrict__ gt, const float* __restrict__ cls_out /*[2]*/,
+          float up_cls, float threshold, const float* __restrict__ vpred /*[B,H,W,3C]*/, const float* __restrict__ centers /*[B,C,3]*/,
+          const float* __restrict__ vtx_out /*[2]*/, float up_vtx, float w_inside, float sigma2, int h, int w, int C, int Cs, int Cv,
+          __nv_bfloat16* __restrict__ d_sc, __nv_bfloat16* __restrict__ d_vt, float* __restrict__ dbias_partial /*[grid][4C]*/)
+{
+    const int H = 8 * h, W = 8 * w, No = 4 * C;
+    const int my = blockIdx.x, n = blockIdx.y;
+    const float s_cls = up_cls / (cls_out[1] + 1e-10f), s_vtx = up_vtx / (vtx_out[1] + 1e-10f);
+    const size_t img = (size_t)n * H * W;
+    extern __shared__ float s_db[];       // [No] bias-gradient sums of the pixels this CTA OWNS (rows 8 my .. 8 my + 7)
+    for (int i = threadIdx.x; i < No; i += blockDim.x) s_db[i] = 0.f;
+    __syncthreads();
+    for (int item = threadIdx.x; item < w * No; item += blockDim.x) {
+        const int mx = item / No, ch = item - mx * No;
+        float acc = 0.f, own = 0.f;
+        for (int ky = 0; ky < 16; ky++) {
+            const int y = 8 * my - 4 + ky;
+            if (y < 0 || y >= H) continue;
+            const float wy = deconv_w(ky, 16);
+            for (int kx = 0; kx < 16; kx++) {
+                const int x = 8 * mx - 4 + kx;
+                if (x < 0 || x >= W) continue;
+                const size_t p = img + (size_t)y * W + x;
+                const int g = __ldg(gt + p);
+                float d = 0.f;
+                if (ch < C) {
+                    if (g >= 0 && g < C) {
+                        const float pg = __ldg(prob + p * C + g);
+                        if (g > 0 || pg < threshold) {
+                            const float pc = ch == g ? pg : __ldg(prob + p * C + ch);
+                            if (__ldg(score + p * C + ch) > 0.f) d = s_cls * (pc - (ch == g ? 1.f : 0.f));
+                        }
+                    }
+                } else {
+                    const int vc = ch - C, c = vc / 3, k = vc - 3 * c;
+                    if (g == c && g > 0) {
+                        const float* cen = centers + ((size_t)n * C + c) * 3;
+                        const float z = cen[2];
+                        if (z > 0.f) {
+                            float t;
+                            if (k == 2) t = (float)log((double)z);
+                            else {
+                                const double dx = (double)cen[0] - (double)x, dy = (double)cen[1] - (double)y;
+                                const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+                                t = (float)((k == 0 ? dx : dy) / nrm);
+                            }
+                            const float diff = w_inside * (__ldg(vpred + p * 3 * C + vc) - t);
+                            const float ad = fabsf(diff);
+                            const float dt = ad < 1.f / sigma2 ? diff * sigma2 : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+                            d = s_vtx * w_inside * dt;
+                        }
+                    }
+                }
+                if (d != 0.f) {
+                    acc = fmaf(wy * deconv_w(kx, 16), d, acc);
+                    if (ky >= 4 && ky < 12 && kx >= 4 && kx < 12) own += d;     // the 8 x 8 pixels of this cell
+                }
+            }
+        }
+        const size_t cell = ((size_t)n * h + my) * w + mx;
+        if (ch < C) d_sc[cell * Cs + ch] = __float2bfloat16_rn(acc);
+        else d_vt[cell * Cv + ch - C] = __float2bfloat16_rn(acc);
+        if (own != 0.f) atomicAdd(&s_db[ch], own);
+    }
+    // zero the padding channels of the two GEMM operands
+    for (int item = threadIdx.x; item < w * (Cs - C); item += blockDim.x) {
+        const int mx = item / (Cs - C), ch = C + item % (Cs - C);
+        d_sc[(((size_t)n * h + my) * w + mx) * Cs + ch] = __float2bfloat16_rn(0.f);
+    }
+    for (int item = threadIdx.x; item < w * (Cv - 3 * C); item += blockDim.x) {
+        const int mx = item / (Cv - 3 * C), ch = 3 * C + item % (Cv - 3 * C);
+        d_vt[(((size_t)n * h + my) * w + mx) * Cv + ch] = __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < No; i += blockDim.x) dbias_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * No + i] = s_db[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_sum_partials(const float* __restrict__ partial, int nparts, int n, float scale, const float* __restrict__ p, float decay, float* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int k = 0; k < nparts; k++) acc += partial[(size_t)k * n + i];
+    acc *= scale;
+    if (p) acc = fmaf(decay, p[i], acc);
+    out[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pose chain (vgg16_convs.py:195-200): poses_pred = l2_normalize(poses_tanh * poses_weight, dim 1); loss = Averagedistance.
+// g = upstream * bottom_diff [N,4C];  u = tanh * w;  nrm = sqrt(max(sum u^2, 1e-12));  p = u / nrm;
+// d u = (g - p (p . g)) / nrm (zero where the clamp is active);  d pre = d u * w * (1 - tanh^2).   One warp per row.
+// Output fp16 [N, ld] (the fc8 backward GEMMs' operand), padding columns zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pose_chain_bwd(const float* __restrict__ g, const float* __restrict__ tanhv, const float* __restrict__ wgt, int N, int D, float upstream,
+                 __half* __restrict__ dpre, int ld)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    float su = 0.f, sg = 0.f;
+    for (int j = lane; j < D; j += 32) {
+        const float u = tanhv[(size_t)row * D + j] * wgt[(size_t)row * D + j];
+        su = fmaf(u, u, su);
+        sg = fmaf(u, upstream * g[(size_t)row * D + j], sg);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); }
+    const bool clamped = su < 1e-12f;
+    const float inv = rsqrtf(fmaxf(su, 1e-12f));
+    for (int j = lane; j < ld; j += 32) {
+        float d = 0.f;
+        if (j < D) {
+            const float t = tanhv[(size_t)row * D + j], wv = wgt[(size_t)row * D + j];
+            const float u = t * wv, gg = upstream * g[(size_t)row * D + j];
+            // p = u * inv; d u = (g - p (p.g)) * inv, (p.g) = sg * inv; with the clamp active the norm is the constant 1e-6
+            const float du = clamped ? gg * inv : (gg - u * inv * (sg * inv)) * inv;
+            d = du * wv * (1.f - t * t);
+        }
+        dpre[(size_t)row * ld + j] = __float2half_rn(fminf(fmaxf(d, -65504.f), 65504.f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SGD with momentum on fp32 master weights + the refreshed 16-bit tensor-core copy
+// ---------------------------------------------------------------------------------------------
+template <typename T16>
+__device__ __forceinline__ T16 to16(float v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+
+template <typename T16>
+__global__ void __launch_bounds__(256)
+k_sgd_momentum(float* __restrict__ w, float* __restrict__ accum, const float* __restrict__ grad, size_t n, float lr, float mu, float wd,
+               float gscale, T16* __restrict__ copy16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        // gradient of loss + wd * |w|^2 / 2 (l2_regularizer on weights and biases, network.py:171-172, 184)
+        const float a = fmaf(mu, accum[i], fmaf(wd, w[i], gscale * grad[i]));
+        accum[i] = a;
+        const float v = fmaf(-lr, a, w[i]);
+        w[i] = v;
+        if (copy16) copy16[i] = to16<T16>(v);
+    }
+}
+
+// out[c][r] = in[r][c] (16-bit elements), tiled through shared memory: the [in][out] copy of a fully connected weight
+// matrix for its input-gradient GEMM
+__global__ void __launch_bounds__(256)
+k_transpose16(const uint16_t* __restrict__ in, int rows, int cols, uint16_t* __restrict__ out)
+{
+    __shared__ uint16_t tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int r = i / 64, c = i % 64;
+        tile[r][c] = (r0 + r < rows && c0 + c < cols) ? in[(size_t)(r0 + r) * cols + c0 + c] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i / 64, r = i % 64;
+        if (c0 + c < cols && r0 + r < rows) out[(size_t)(c0 + c) * rows + r0 + r] = tile[r][c];
+    }
+}
+
+// 16-bit conversions of small gradient tensors (fp16 <-> bf16 <-> f32): dst[i] = (T)src[i]
+__global__ void __launch_bounds__(256)
+k_half_to_float(const __half* __restrict__ src, size_t n, float* __restrict__ dst)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+}
+
+// conv1_1 weight gradient (Cin = 3: below any tensor-core tile): dW[co][tap * 3 + c] = sum_pix x[pix + tap][c] * dz[pix][co],
+// x = uint8 BGR - mean (zero outside the image).  Fixed grid; every CTA loops over 256-pixel chunks, thread = (co, tap group).
+__global__ void __launch_bounds__(256)
+k_conv1_wgrad(const unsigned char* __restrict__ img /*[B,H,W,3]*/, const __nv_bfloat16* __restrict__ dz /*[B,H,W,64]*/, int B, int H, int W,
+              float m0, float m1, float m2, float* __restrict__ partial /*[grid][64][27]*/)
+{
+    __shared__ float s_patch[256][28];
+    const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;       // 4 tap groups: k in [7 tg, min(7 tg + 7, 27))
+    const int k_lo = 7 * tg, k_hi = min(k_lo + 7, 27);
+    float acc[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) acc[j] = 0.f;
+    const size_t npix = (size_t)B * H * W;
+    for (size_t base = (size_t)blockIdx.x * 256; base < npix; base += (size_t)gridDim.x * 256) {
+        __syncthreads();
+        {   // stage the 27 input values of 256 pixels (thread = pixel)
+            const size_t p = base + threadIdx.x;
+            if (p < npix) {
+                const int x = (int)(p % W), y = (int)((p / W) % H);
+                const size_t n = p / ((size_t)W * H);
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                    const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                    const unsigned char* q = img + ((n * H + yy) * W + xx) * 3;
+                    s_patch[threadIdx.x][tap * 3 + 0] = ok ? (float)q[0] - m0 : 0.f;
+                    s_patch[threadIdx.x][tap * 3 + 1] = ok ? (float)q[1] - m1 : 0.f;
+                    s_patch[threadIdx.x][tap * 3 + 2] = ok ? (float)q[2] - m2 : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        const int cnt = (int)min((size_t)256, npix - base);
+        for (int i = 0; i < cnt; i++) {
+            const float d = __bfloat162float(dz[(base + i) * 64 + co]);
+            if (d == 0.f) continue;
+#pragma unroll
+            for (int j = 0; j < 7; j++)
+                if (k_lo + j < k_hi) acc[j] = fmaf(s_patch[i][k_lo + j], d, acc[j]);
+        }
+    }
+    for (int j = 0; j < 7; j++)
+        if (k_lo + j < k_hi) partial[((size_t)blockIdx.x * 64 + co) * 27 + k_lo + j] = acc[j];
+}
+
+}  // namespace pcnn
+
+using namespace pcnn;
+
+static int ew_blocks(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 8); }
+
+extern "C" int pcnn_add_up2_bf16(const void* a4, const void* a5, int B, int h, int w, int C, void* out, void* stream)
+{
+    PCNN_REQUIRE(a4 && a5 && out && h % 2 == 0 && w % 2 == 0, "add_up2: bad arguments");
+    k_add_up2<<<ew_blocks((size_t)B * h * w * C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a4, (const __nv_bfloat16*)a5, B, h, w, C,
+                                                                                (__nv_bfloat16*)out);
+    return check_launch("add_up2");
+}
+
+extern "C" int pcnn_up2_bwd_bf16(const void* dadd, const void* y5, int B, int h, int w, int C, void* d5, void* stream)
+{
+    PCNN_REQUIRE(dadd && d5 && h % 2 == 0 && w % 2 == 0, "up2_bwd: bad arguments");
+    k_up2_bwd<<<ew_blocks((size_t)B * (h / 2) * (w / 2) * C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dadd, (const __nv_bfloat16*)y5, B, h,
+                                                                                            w, C, (__nv_bfloat16*)d5);
+    return check_launch("up2_bwd");
+}
+
+extern "C" int pcnn_pack_lowres(const void* sc, int Cs, const void* vt, int Cv, int B, int h, int w, int C, float* lowres, void* stream)
+{
+    PCNN_REQUIRE(sc && vt && lowres && Cs >= C && Cv >= 3 * C, "pack_lowres: bad arguments");
+    const size_t npix = (size_t)B * h * w;
+    k_pack_lowres<<<ew_blocks(npix * 4 * C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)sc, Cs, (const __nv_bfloat16*)vt, Cv, npix, C, lowres);
+    return check_launch("pack_lowres");
+}
+
+// d bias_score [C] and d bias_vertex [3C] come back in dbias [4C]; workspace: B * h * 4C floats
+extern "C" int pcnn_up8_heads_bwd(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
+                                  float threshold, const float* vertex_pred, const float* centers, const float* vertex_loss_out,
+                                  float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C, int Cs, int Cv,
+                                  void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(prob && score && gt && cls_loss_out && vertex_pred && centers && vertex_loss_out && d_sc_bf16 && d_vt_bf16 && dbias && workspace,
+                 "up8_heads_bwd: NULL tensor pointer");
+    PCNN_REQUIRE(Cs >= C && Cv >= 3 * C && h <= 65535 && B <= 65535, "up8_heads_bwd: bad shape");
+    const size_t need = sizeof(float) * (size_t)B * h * 4 * C;
+    PCNN_REQUIRE(workspace_bytes >= need, "up8_heads_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(h, B);
+    k_up8_bwd<<<grid, 256, sizeof(float) * 4 * C, st>>>(prob, score, gt, cls_loss_out, upstream_cls, threshold, vertex_pred, centers, vertex_loss_out,
+                                                       upstream_vertex, w_inside, sigma * sigma, h, w, C, Cs, Cv, (__nv_bfloat16*)d_sc_bf16,
+                                                       (__nv_bfloat16*)d_vt_bf16, (float*)workspace);
+    k_sum_partials<<<(4 * C + 255) / 256, 256, 0, st>>>((const float*)workspace, B * h, 4 * C, 1.f, nullptr, 0.f, dbias);
+    return check_launch("up8_heads_bwd");
+}
+
+extern "C" int pcnn_pose_chain_bwd(const float* bottom_diff, const float* poses_tanh, const float* poses_weight, int N, int D, float upstream,
+                                   void* dpre_f16, int ld, void* stream)
+{
+    PCNN_REQUIRE(bottom_diff && poses_tanh && poses_weight && dpre_f16 && N >= 1 && D >= 1 && ld >= D, "pose_chain_bwd: bad arguments");
+    k_pose_chain_bwd<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(bottom_diff, poses_tanh, poses_weight, N, D, upstream, (__half*)dpre_f16, ld);
+    return check_launch("pose_chain_bwd");
+}
+
+// accum = mu * accum + (gscale * grad + wd * w); w -= lr * accum; copy16 (optional) = the refreshed tensor-core copy, kind 0 = bf16, 1 = fp16
+extern "C" int pcnn_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float lr, float mu, float wd, float gscale, void* copy16,
+                                 int kind, void* stream)
+{
+    PCNN_REQUIRE(w && accum && grad, "sgd_momentum: NULL tensor pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 1) k_sgd_momentum<__half><<<ew_blocks(n), 256, 0, st>>>(w, accum, grad, n, lr, mu, wd, gscale, (__half*)copy16);
+    else k_sgd_momentum<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(w, accum, grad, n, lr, mu, wd, gscale, (__nv_bfloat16*)copy16);
+    return check_launch("sgd_momentum");
+}
+
+extern "C" int pcnn_transpose16(const void* in, int rows, int cols, void* out, void* stream)
+{
+    PCNN_REQUIRE(in && out && rows >= 1 && cols >= 1, "transpose16: bad arguments");
+    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+    k_transpose16<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in, rows, cols, (uint16_t*)out);
+    return check_launch("transpose16");
+}
+
+extern "C" int pcnn_half_to_float(const void* src_f16, size_t n, float* dst, void* stream)
+{
+    PCNN_REQUIRE(src_f16 && dst, "half_to_float: NULL tensor pointer");
+    k_half_to_float<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, n, dst);
+    return check_launch("half_to_float");
+}
+
+// conv1_1 weight gradient: img [B,H,W,3] u8, dz [B,H,W,64] bf16 -> dW [64][27] f32 = scale * gradient (+ decay * w); workspace 592*64*27 floats
+extern "C" int pcnn_conv1_wgrad(const void* img_u8, const float* mean3_host, const void* dz_bf16, int B, int H, int W, float scale,
+                                const float* w, float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(img_u8 && dz_bf16 && dW && workspace, "conv1_wgrad: NULL tensor pointer");
+    const int grid = kNumSMs * 4;
+    PCNN_REQUIRE(workspace_bytes >= sizeof(float) * (size_t)grid * 64 * 27, "conv1_wgrad: workspace too small");
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    if (mean3_host) { m0 = mean3_host[0]; m1 = mean3_host[1]; m2 = mean3_host[2]; }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_conv1_wgrad<<<grid, 256, 0, st>>>((const unsigned char*)img_u8, (const __nv_bfloat16*)dz_bf16, B, H, W, m0, m1, m2, (float*)workspace);
+    k_sum_partials<<<(64 * 27 + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, 64 * 27, scale, w, decay, dW);
+    return check_launch("conv1_wgrad");
+}

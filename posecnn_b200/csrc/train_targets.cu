@@ -81,6 +81,35 @@ k_loss_cls_hard(const float* __restrict__ score /*log-softmax*/, const float* __
     }
 }
 
+// same loss from the RAW scores (the `score` layer output): log-softmax of the labelled class computed per selected pixel
+// (network.py:491-506: x - max - log sum exp(x - max)), so the [B,H,W,C] log-probability tensor is never materialised
+__global__ void __launch_bounds__(kLossThreads)
+k_loss_cls_hard_raw(const float* __restrict__ score_raw, const float* __restrict__ prob, const int* __restrict__ gt, unsigned npix, int C,
+                    float threshold, double* __restrict__ partial, unsigned* __restrict__ ticket, float* __restrict__ out)
+{
+    __shared__ double sh[2 * kLossThreads / 32];
+    double s = 0, n = 0;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int g = __ldg(gt + p);
+        if (g < 0 || g >= C) continue;
+        if (g > 0 || __ldg(prob + (size_t)p * C + g) < threshold) {
+            const float* sp = score_raw + (size_t)p * C;
+            float m = __ldg(sp);
+            for (int c = 1; c < C; c++) m = fmaxf(m, __ldg(sp + c));
+            float se = 0.f;
+            for (int c = 0; c < C; c++) se += expf(__ldg(sp + c) - m);
+            s -= (double)(__ldg(sp + g) - m - logf(se));
+            n += 1.0;
+        }
+    }
+    block_reduce2(s, n, sh);
+    double ts, tn;
+    if (finish_partials(s, n, partial, ticket, ts, tn)) {
+        out[0] = (float)(ts / (tn + 1e-10));
+        out[1] = (float)tn;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_loss_cls_hard_grad(const float* __restrict__ prob, const int* __restrict__ gt, unsigned npix, int C, float threshold,
                      const float* __restrict__ loss_out, float upstream, float* __restrict__ grad /*[npix, C]*/)
@@ -218,7 +247,8 @@ k_vertex_targets_instances(const int* __restrict__ label, const int* __restrict_
 // ---------------------------------------------------------------------------------------------
 __device__ void mat2quat_d(const float* __restrict__ rt /*3x4 row-major*/, float q[4])
 {
-    const double Qxx = rt[0], Qxy = rt[1], Qxz = rt[2], Qyx = rt[4], Qyy = rt[5], Qyz = rt[6], Qzx = rt[8], Qzy = rt[9], Qzz = rt[10];
+    // transforms3d: `Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz = M.flat` (row-major flat order: Qyx = M[0][1], Qxy = M[1][0], ...)
+    const double Qxx = rt[0], Qyx = rt[1], Qzx = rt[2], Qxy = rt[4], Qyy = rt[5], Qzy = rt[6], Qxz = rt[8], Qyz = rt[9], Qzz = rt[10];
     double A[4][4] = {{Qxx - Qyy - Qzz, Qyx + Qxy, Qzx + Qxz, Qyz - Qzy},
                       {Qyx + Qxy, Qyy - Qxx - Qzz, Qzy + Qyz, Qzx - Qxz},
                       {Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, Qxy - Qyx},
@@ -456,4 +486,19 @@ extern "C" int pcnn_pack_pose_meta_fwd(const float* poses, const int32_t* cls, c
     PCNN_REQUIRE(B >= 1 && I >= 1 && B * I <= 1024, "pack_pose_meta: at most 1024 instance slots per batch (got %d x %d)", B, I);
     k_pack_pose_meta<<<1, 256, 0, (cudaStream_t)stream>>>(poses, cls, intrinsics, B, I, im_scale, flip_x, pose_blob, num_rows, meta);
     return check_launch("pack_pose_meta");
+}
+
+extern "C" int pcnn_loss_cls_hard_raw_fwd(const float* score_raw, const float* prob, const int32_t* gt, int B, int H, int W, int C,
+                                          float threshold, float* loss_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(score_raw && prob && gt && loss_out && workspace, "loss_cls_hard_raw: NULL tensor pointer");
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "loss_cls_hard_raw: too many pixels");
+    size_t need = 0;
+    pcnn_train_loss_workspace_bytes(&need);
+    PCNN_REQUIRE(workspace_bytes >= need, "loss_cls_hard_raw: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* partial = (double*)workspace;
+    unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
+    k_loss_cls_hard_raw<<<kLossBlocks, kLossThreads, 0, (cudaStream_t)stream>>>(score_raw, prob, gt, (unsigned)B * H * W, C, threshold, partial, ticket,
+                                                                                loss_out);
+    return check_launch("loss_cls_hard_raw");
 }

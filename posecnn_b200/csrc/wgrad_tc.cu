@@ -44,6 +44,7 @@ struct WgParams {
     int tiles_w, tiles_h, ktiles;          // K tiles = B * tiles_h * tiles_w
     int ktiles_per_split, splits;
     int n_tile, n_tiles, m_tiles;          // N tile (64 / 128 / 256), Cin / n_tile, ceil(Cout / 128)
+    int f16;                               // operands are FP16 (the fully connected head) instead of BF16
 };
 
 // MN-major, 128-byte-swizzled operand: K rows of 128 B (64 channels), 8-row groups 1024 B apart (SBO), 64-channel
@@ -59,10 +60,10 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
     return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc_mn(int n)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n, int f16)
 {
-    // c F32, a = b = BF16, a_major = b_major = MN (bits 15, 16), N >> 3 @17, M = 128 >> 4 @24
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // c F32, a = b = BF16 (format 1) or F16 (format 0), a_major = b_major = MN (bits 15, 16), N >> 3 @17, M = 128 >> 4 @24
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -136,7 +137,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
         }
     } else if (warp == 5) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_mn(p.n_tile);
+            const uint32_t idesc = make_idesc_mn(p.n_tile, p.f16);
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < nk; k++) {
@@ -368,6 +369,7 @@ static int make_map_nhwc_box(CUtensorMap* m, const void* ptr, int B, int H, int 
 
 static int plan(int B, int H, int W, int Cin, int Cout, int ksize, WgParams* p)
 {
+    p->f16 = 0;
     p->B = B; p->H = H; p->W = W; p->Cin = Cin; p->Cout = Cout; p->ksize = ksize; p->taps = ksize * ksize;
     // pixel box: 16 x 4 for images, 64 x 1 for "row lists" (H == 1: fully connected layers), 8 x 8 for narrow maps
     if (H == 1) { p->bw = 64; p->bh = 1; }
@@ -405,9 +407,25 @@ extern "C" int pcnn_conv_wgrad_workspace_bytes(int B, int H, int W, int Cin, int
 }
 
 // x [B,H,W,Cin] bf16, dz [B,H,W,Cout] bf16 -> dW [Cout][ksize*ksize*Cin] f32 = scale * sum_pixels x (*) dz (+ decay * w if w != NULL)
+static int wgrad_impl(const void* x_bf16, const void* dz_bf16, int B, int H, int W, int Cin, int Cout, int ksize, float scale,
+                      const float* w_f32, float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream, int f16);
+
 extern "C" int pcnn_conv_wgrad_bf16_tc(const void* x_bf16, const void* dz_bf16, int B, int H, int W, int Cin, int Cout, int ksize,
                                        float scale, const float* w_f32, float decay, float* dW, void* workspace, size_t workspace_bytes,
                                        void* stream)
+{
+    return wgrad_impl(x_bf16, dz_bf16, B, H, W, Cin, Cout, ksize, scale, w_f32, decay, dW, workspace, workspace_bytes, stream, 0);
+}
+
+// fully connected layer: x [rows, Cin] fp16, dy [rows, Cout] fp16 -> dW [Cout][Cin] f32 (workspace: pcnn_conv_wgrad_workspace_bytes(1, 1, rows, ...))
+extern "C" int pcnn_fc_wgrad_f16_tc(const void* x_f16, const void* dy_f16, int rows, int Cin, int Cout, float scale, const float* w_f32,
+                                    float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return wgrad_impl(x_f16, dy_f16, 1, 1, rows, Cin, Cout, 1, scale, w_f32, decay, dW, workspace, workspace_bytes, stream, 1);
+}
+
+static int wgrad_impl(const void* x_bf16, const void* dz_bf16, int B, int H, int W, int Cin, int Cout, int ksize, float scale,
+                      const float* w_f32, float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream, int f16)
 {
     PCNN_REQUIRE(x_bf16 && dz_bf16 && dW && workspace, "conv_wgrad: NULL tensor pointer");
     size_t need = 0;
@@ -416,6 +434,7 @@ extern "C" int pcnn_conv_wgrad_bf16_tc(const void* x_bf16, const void* dz_bf16, 
     if (workspace_bytes < need) { set_error("conv_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need); return PCNN_E_WORKSPACE; }
     WgParams p;
     plan(B, H, W, Cin, Cout, ksize, &p);
+    p.f16 = f16;
     CUtensorMap mx, mz;
     rc = make_map_nhwc_box(&mx, x_bf16, B, H, W, Cin, p.bw, p.bh);
     if (rc) return rc;

@@ -112,7 +112,7 @@ extern "C" int umma_probe_mn(const void* A /*[80][128] bf16*/, const void* B /*[
     cuuint64_t db[2] = {64, kRows}, sb[1] = {128}; cuuint32_t bb[2] = {64, kRows};
     if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)B, db, sb, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) return -3;
     cudaFuncSetAttribute(k_probe_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
-    k_probe_mn<<<1, 128, 3 * kBlk + 2048>>>(ma, mb, out);
+    k_probe_mn<<<1, 128, 3 * kBlk + 4096>>>(ma, mb, out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("probe_mn: %s\n", cudaGetErrorString(e)); return -4; }
     return 0;
