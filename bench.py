@@ -636,6 +636,91 @@ def run_project(args, rank, world, local):
 
 
 # ------------------------------------------------------------------------------------------
+# Training step (BASELINE configs[4]): forward + backward + SGD-momentum update of the whole network with hard_label cross entropy,
+# vertex smooth-L1 and average_distance_loss, ONE global batch of B frames sharded over the GPUs, gradients all-reduced over NCCL
+# ------------------------------------------------------------------------------------------
+def run_train(args, rank, world, local):
+    import torch
+    from posecnn_b200 import parallel, synth
+    from posecnn_b200.networks.vgg16_convs import vgg16_convs
+    from posecnn_b200.train import Trainer
+    dev = torch.device("cuda", local)
+    Bg = args.batch
+    off, Bl = parallel.shard_range(Bg, rank, world)
+    net = vgg16_convs(num_classes=C, device=dev, is_train=True, fold_vertex_head=False).init_random(seed=0)
+    # O(1) logits / pre-activations, as a trained network has (a Kaiming-initialised output layer saturates softmax and tanh)
+    net.params["score/weights"] *= 0.02; net.params["vertex_pred/weights"] *= 0.02; net.params["fc8/weights"] *= 0.01
+    net.prepare()
+    tr = Trainer(net, lr=1e-4, momentum=0.9, weight_decay=1e-4, vertex_w=1.0, vertex_w_inside=10.0, margin=0.01, world=world)
+    nu = min(Bg, 8)
+    sc = synth.make_scene(batch=nu, height=H, width=W, num_classes=C, seed=4234, other_channel_noise=False)
+    reps = -(-Bg // nu)
+    label_all = np.concatenate([sc["label"]] * reps, 0)[:Bg]
+    centers = np.zeros((nu, C, 3), np.float32)
+    for (b, cls, cx, cy, z) in sc["centers"]:
+        centers[b, cls] = (cx, cy, z)
+    centers_all = np.concatenate([centers] * reps, 0)[:Bg]
+    gts = []
+    for r_ in range(reps):
+        g = sc["gt"].copy(); g[:, 0] += r_ * nu; gts.append(g)
+    gt_all = np.concatenate(gts, 0); gt_all = gt_all[gt_all[:, 0] < Bg]
+    rgb, _ = synth.make_images(Bg, H, W, seed=21)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    data, gtl, cen = T(rgb[off:off + Bl]), T(label_all[off:off + Bl]), T(centers_all[off:off + Bl])
+    meta = T(np.stack([synth.make_meta(synth.intrinsics(H, W))] * Bl)); ext = T(synth.extents_for(C)); gtp = T(gt_all)
+    pts = T(synth.make_model_points(C, 2620)); sym = T(synth.LOV_SYMMETRY)
+    h_img = torch.from_numpy(rgb[off:off + Bl]).pin_memory(); h_lab = torch.from_numpy(label_all[off:off + Bl]).pin_memory()
+
+    def step(d, l):
+        return tr.step(d, l, cen, meta, ext, gtp, pts, sym, batch_global=Bg, batch_offset=off)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        out = step(data, gtl)
+    torch.cuda.synchronize(); barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(data, gtl)
+    e1.record()
+    torch.cuda.synchronize(); barrier(world)
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
+    # end to end: pinned host images + label maps in, the loss scalar out, every step
+    d_in, l_in = torch.empty_like(data), torch.empty_like(gtl)
+    h_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+    k = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        d_in.copy_(h_img, non_blocking=True); l_in.copy_(h_lab, non_blocking=True)
+        o = step(d_in, l_in)
+        h_loss.copy_(o["loss"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    dt = max_over_ranks((time.perf_counter() - t0) / k, world)
+    peaks = measured_peaks()
+    flop = 3.0 * VGG_FLOP_PER_FRAME * Bl                      # forward + input-gradient + weight-gradient GEMMs of the trunk
+    tf = flop / (ms_step * 1e-3) / 1e12
+    sust = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    return dict(
+        metric="frames/sec, training step (VGG16 + heads + Hough + ROI pose head, hard_label + vertex + average_distance losses, SGD momentum)",
+        value=Bg / (ms_step * 1e-3), unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+        higher_is_better=True, scaling="strong", vs_baseline=None,
+        dtype="bf16 operands / fp32 accumulate (convolutions fwd + dgrad + wgrad), fp16 operands (fc6-fc8), fp32 master weights / losses", data="synthetic",
+        config=dict(workload="configs[4]: training step, ONE global batch of %d 640x480 frames, synthetic YCB-shaped labels / poses, 22 classes, "
+                             "keep_prob 1.0" % Bg, global_batch=Bg, per_gpu_batch=Bl,
+                    parallelism="image shards x%d, global loss normalisers, per-tensor NCCL all-reduce (SUM) of the gradients on a side stream" % world,
+                    l2="no flush: %.1f GB of saved activations per step (>> 126 MB L2)" % (0.31 * Bl), rois_rows=int(out["num_rois"].item()),
+                    losses=dict(cls=float(out["loss_cls"].item()), vertex=float(out["loss_vertex"].item()), pose=float(out["loss_pose"].item()))),
+        clocks=clocks, gpu_launches=None,
+        roofline=dict(bound="tensor", achieved=tf, peak=sust, unit="TFLOP/s", frac=tf / sust, traffic=None, peak_source=peaks["source"] + " (sustained: a kernel "
+                      "group inside a long step)", kernel="trunk GEMMs: 13 forward convolutions + 12 dgrad (k_conv_tc / k_conv_row2) + 12 wgrad (k_wgrad_tc)",
+                      note="achieved = 3 x 187.918 GFLOP/frame x this rank's frames / WHOLE step time (heads, losses, pose head, update included)"),
+        e2e=dict(value=Bg / dt, unit="frames/s", h2d_bytes_per_step=int(h_img.numel() + h_lab.numel() * 4), d2h_bytes_per_step=4,
+                 note="pinned host uint8 images + int32 label maps in, loss scalar out; wall clock over %d steps" % k))
+
+
+# ------------------------------------------------------------------------------------------
 # CPU arm: the same path restated on the host cores (oracle/cpu_pipeline.py)
 # ------------------------------------------------------------------------------------------
 def cpu_pipeline_sample(frames_per_step, steps, warmup, threads=None):
@@ -723,7 +808,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="full", choices=["hough", "full", "rgbd", "project"])
+    ap.add_argument("--workload", default="full", choices=["hough", "full", "rgbd", "project", "train"])
     ap.add_argument("--batch", type=int, default=32, help="frames of the GLOBAL batch per step (sharded over the GPUs)")
     ap.add_argument("--grid", type=int, default=128, help="voxel grid size of --workload project")
     ap.add_argument("--e2e-batch", type=int, default=32)
@@ -746,6 +831,10 @@ def main():
         res = run_hough(args, rank, world, local)
     elif args.workload == "project":
         res = run_project(args, rank, world, local)
+    elif args.workload == "train":
+        if args.batch == 32:
+            args.batch = 64                                   # configs[4] names batch 64
+        res = run_train(args, rank, world, local)
     else:
         res, net = run_full(args, rank, world, local, "RGBD" if args.workload == "rgbd" else "COLOR")
         if rank == 0 and world == 1 and args.workload == "full" and not args.no_hough_record:
