@@ -250,7 +250,7 @@ int pcnn_loss_cls_hard_raw_fwd(const float* score_raw, const float* prob, const 
 int pcnn_fc_dgrad_f16_tc(const void* dy_f16, const void* w_in_out_f16, int M, int N, int K, const void* relu_mask_f16, void* out_f16,
                          int ld_out, void* workspace, size_t workspace_bytes, void* stream);
 int pcnn_transpose16(const void* in, int rows, int cols, void* out, void* stream);
-int pcnn_half_to_float(const void* src_f16, size_t n, float* dst, void* stream);
+int pcnn_half_to_float(const void* src_f16, size_t n, float scale, float* dst, void* stream);
 int pcnn_conv1_wgrad(const void* img_u8, const float* mean3_host, const void* dz_bf16, int B, int H, int W, float scale,
                      const float* w, float decay, float* dW, void* workspace, size_t workspace_bytes, void* stream);
 

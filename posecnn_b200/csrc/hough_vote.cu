@@ -30,6 +30,7 @@
 //              reference kernel, done only for selected cells)
 //   k_finalize ROI cap, row offsets, ROI / pose / target / weight / domain rows
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -441,7 +442,7 @@ k_worklist(int B, int C, int R, int nbands, const int* __restrict__ img_count, c
 // k_vote: persistent CTAs; one (image, class, band) difference array in shared memory
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4)
-k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restrict__ slot_cls,
+k_vote(int H, int W, int C, int R, int nbands, float inlier, float tau0, const int* __restrict__ slot_cls,
        const int* __restrict__ cls_nsamp, const int* __restrict__ cls_soff, const int* __restrict__ bbox,
        const Sample* __restrict__ samples, int samp_cap, const int* __restrict__ work, int* __restrict__ work_ctr,
        int2* __restrict__ band_res, float* __restrict__ votes_out)
@@ -582,7 +583,7 @@ k_vote(int H, int W, int C, int R, int nbands, float inlier, const int* __restri
                             // The ray estimate and the fp32 predicate both sit within ~1e-6 (dy^2 + m^2) / |dy| cells
                             // of the real cone boundary; an end point closer than tau to an integer
                             // is re-checked with the reference predicate, the others are exact as they are.
-                            const float tau = 0.03f + 2e-6f * __fdividef(dy * dy + fm2, fabsf(dy));
+                            const float tau = tau0 + 2e-6f * __fdividef(dy * dy + fm2, fabsf(dy));
                             if (a > e) {
                                 const bool ca = (float)(a - x) - hi < tau && a >= wmin && a <= wmax;
                                 const bool ce = lo - (float)(e - x) < tau && e >= wmin && e <= wmax;
@@ -1011,7 +1012,11 @@ static int run_front(const Layout& L, char* ws, const int32_t* label, const Vert
     k_worklist<<<1, 1024, 0, st>>>(B, C, L.R, L.nbands, img_count, slot_cls, cls_nsamp, bbox, work, work_ctr);
     size_t smem = sizeof(int) * (size_t)L.R * (W + 3);
     PCNN_SMEM_OPTIN(k_vote, 110 * 1024, "hough k_vote");
-    k_vote<<<4 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, slot_cls, cls_nsamp, cls_soff, bbox,
+    // end points closer than tau0 (+ a term growing with the distance) to a cell centre are re-checked with the reference
+    // predicate; the estimate's own error is ~1e-4 cells, the default keeps a 40x margin (sweep 0.03 .. 0.002: all parity
+    // tests identical, 0.438 -> 0.393 ms at batch 32, profiles/r02_hough_tau_sweep.txt)
+    static const float tau0 = getenv("PCNN_HOUGH_TAU0") ? (float)atof(getenv("PCNN_HOUGH_TAU0")) : 0.004f;
+    k_vote<<<4 * kNumSMs, kThreads, smem, st>>>(H, W, C, L.R, L.nbands, inlier, tau0, slot_cls, cls_nsamp, cls_soff, bbox,
                                                 samples, L.samp_cap, work, work_ctr, band_res, votes_out);
     return check_launch("hough front kernels");
 }

@@ -275,9 +275,9 @@ k_transpose16(const uint16_t* __restrict__ in, int rows, int cols, uint16_t* __r
 
 // 16-bit conversions of small gradient tensors (fp16 <-> bf16 <-> f32): dst[i] = (T)src[i]
 __global__ void __launch_bounds__(256)
-k_half_to_float(const __half* __restrict__ src, size_t n, float* __restrict__ dst)
+k_half_to_float(const __half* __restrict__ src, size_t n, float scale, float* __restrict__ dst)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = scale * __half2float(src[i]);
 }
 
 // conv1_1 weight gradient (Cin = 3: below any tensor-core tile): dW[co][tap * 3 + c] = sum_pix x[pix + tap][c] * dz[pix][co],
@@ -402,10 +402,10 @@ extern "C" int pcnn_transpose16(const void* in, int rows, int cols, void* out, v
     return check_launch("transpose16");
 }
 
-extern "C" int pcnn_half_to_float(const void* src_f16, size_t n, float* dst, void* stream)
+extern "C" int pcnn_half_to_float(const void* src_f16, size_t n, float scale, float* dst, void* stream)
 {
     PCNN_REQUIRE(src_f16 && dst, "half_to_float: NULL tensor pointer");
-    k_half_to_float<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, n, dst);
+    k_half_to_float<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>((const __half*)src_f16, n, scale, dst);
     return check_launch("half_to_float");
 }
 

@@ -53,6 +53,7 @@ class Trainer:
         self.net, self.lr, self.mu, self.wd = net, float(lr), float(momentum), float(weight_decay)
         self.vertex_w, self.w_inside, self.margin, self.world = float(vertex_w), float(vertex_w_inside), float(margin), int(world)
         self.C = net.num_classes
+        self.pose_loss_scale = 4096.0            # loss scale of the fp16 pose-head backward (see backward())
         self.comm = torch.cuda.Stream(device=net.device) if world > 1 else None
         P, dev = net.params, net.device
         C = self.C
@@ -224,14 +225,14 @@ class Trainer:
         check(lib().pcnn_fc_dgrad_f16_tc(ptr(dy), ptr(wt), M_, N, K, ptr(mask), ptr(out), N, ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
         return out
 
-    def _fc_wgrad(self, x, dy):
+    def _fc_wgrad(self, x, dy, scale=1.0):
         rows, Cin = x.shape
         Cout = dy.shape[1]
         out = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
         nbytes = ctypes.c_size_t(0)
         check(lib().pcnn_conv_wgrad_workspace_bytes(1, 1, rows, Cin, Cout, 1, ctypes.byref(nbytes)))
         ws = workspace("wgrad", nbytes.value, x.device)
-        check(lib().pcnn_fc_wgrad_f16_tc(ptr(x), ptr(dy), rows, Cin, Cout, f32(1.0), ptr(None), f32(0.0), ptr(out), ptr(ws),
+        check(lib().pcnn_fc_wgrad_f16_tc(ptr(x), ptr(dy), rows, Cin, Cout, f32(scale), ptr(None), f32(0.0), ptr(out), ptr(ws),
                                          ctypes.c_size_t(ws.numel()), stream()))
         return out
 
@@ -257,21 +258,25 @@ class Trainer:
         pose_scale = (float(rows) / rows_global).item() if self.world > 1 else 1.0
         A["loss_pose"] = A["loss_pose_raw"] * pose_scale
         # ---- pose head
+        # The head's backward GEMMs run on FP16 operands like its forward.  The pose-loss gradients are tiny (a mean over rows x points:
+        # 1e-6 .. 1e-4 per element, below fp16's normal range), so the chain is LOSS-SCALED by S = 2^12 where it enters fp16 and un-scaled
+        # where it leaves (weight gradients, bias sums, the RoiPool gradient); conversions saturate at +-65504.
+        S = self.pose_loss_scale
         D = 4 * C
         dpre = torch.empty((rows, 128), dtype=torch.float16, device=dev)
-        check(lib().pcnn_pose_chain_bwd(ptr(A["pose_diff"]), ptr(A["poses_tanh"]), ptr(A["poses_weight"]), rows, D, f32(pose_scale), ptr(dpre), 128,
+        check(lib().pcnn_pose_chain_bwd(ptr(A["pose_diff"]), ptr(A["poses_tanh"]), ptr(A["poses_weight"]), rows, D, f32(pose_scale * S), ptr(dpre), 128,
                                         stream()))
-        self._emit(grads, "fc8/w", self._fc_wgrad(A["fc7"], dpre))
-        self._emit(grads, "fc8/b", dpre[:, :D].float().sum(0))
+        self._emit(grads, "fc8/w", self._fc_wgrad(A["fc7"], dpre, 1.0 / S))
+        self._emit(grads, "fc8/b", dpre[:, :D].float().sum(0) / S)
         d7 = self._fc_dgrad(dpre, "fc8", A["fc7"])
-        self._emit(grads, "fc7/w", self._fc_wgrad(A["fc6"], d7))
-        self._emit(grads, "fc7/b", d7.float().sum(0))
+        self._emit(grads, "fc7/w", self._fc_wgrad(A["fc6"], d7, 1.0 / S))
+        self._emit(grads, "fc7/b", d7.float().sum(0) / S)
         d6 = self._fc_dgrad(d7, "fc7", A["fc6"])
-        self._emit(grads, "fc6/w", self._fc_wgrad(A["pool"], d6))
-        self._emit(grads, "fc6/b", d6.float().sum(0))
+        self._emit(grads, "fc6/w", self._fc_wgrad(A["pool"], d6, 1.0 / S))
+        self._emit(grads, "fc6/b", d6.float().sum(0) / S)
         dpool16 = self._fc_dgrad(d6, "fc6", None)                                              # [rows, 25088]
         dpool = torch.empty((rows, 7, 7, 512), dtype=torch.float32, device=dev)
-        check(lib().pcnn_half_to_float(ptr(dpool16), ctypes.c_size_t(dpool16.numel()), ptr(dpool), stream()))
+        check(lib().pcnn_half_to_float(ptr(dpool16), ctypes.c_size_t(dpool16.numel()), f32(1.0 / S), ptr(dpool), stream()))
         g5_roi = roi_pooling_op.roi_pool_grad(A["conv5_3"], A["rois"], A["a5"], dpool, 7, 7, 1.0 / 16.0, 0)       # fp32 dense
         g4_roi = roi_pooling_op.roi_pool_grad(A["conv4_3"], A["rois"], A["a4"], dpool, 7, 7, 1.0 / 8.0, 0)
         # ---- FCN heads

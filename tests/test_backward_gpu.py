@@ -88,3 +88,23 @@ def test_conv_dgrad_through_forward_kernel(cuda, Cin, Cout, k):
     got = conv.conv_bf16(dz, conv.hwio_to_tc_dgrad(w), torch.zeros(Cin, device=cuda), k, False)
     e = rel_l2(got.float(), x.grad.permute(0, 2, 3, 1))
     assert e < 5e-3, e                                                        # one bf16 rounding of the output
+
+
+def test_conv1_wgrad_cuda_cores(cuda):
+    """conv1_1 weight gradient (Cin = 3, input = uint8 image - mean) against autograd on the same bf16 dz."""
+    import ctypes
+    from posecnn_b200._lib import check, f32, lib, ptr, stream, workspace
+    g = torch.Generator().manual_seed(7)
+    B, H, W = 2, 20, 28
+    img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(cuda)
+    dz = (torch.randn(B, H, W, 64, generator=g) * 0.1).to(torch.bfloat16).to(cuda)
+    mean = (102.9801, 115.9465, 122.7717)
+    x = (img.float() - torch.tensor(mean, device=cuda)).permute(0, 3, 1, 2)
+    w = torch.zeros(64, 3, 3, 3, device=cuda, requires_grad=True)
+    F.conv2d(x, w, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    want = w.grad.permute(0, 2, 3, 1).reshape(64, 27)                       # [co][tap * 3 + c]
+    got = torch.empty((64, 27), device=cuda)
+    ws = workspace("conv1_wgrad", 4 * 148 * 4 * 64 * 27, cuda)
+    m = (ctypes.c_float * 3)(*mean)
+    check(lib().pcnn_conv1_wgrad(ptr(img), m, ptr(dz), B, H, W, f32(1.0), ptr(None), f32(0.0), ptr(got), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    assert rel_l2(got, want) < 1e-5

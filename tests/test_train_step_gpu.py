@@ -64,13 +64,49 @@ def make_problem(cuda, B=2, H=64, W=96, C=6, seed=0):
     return net, T(rgb), T(sc["label"]), T(centers), T(sc["meta"].reshape(B, 48)), T(sc["extents"]), T(sc["gt"]), T(pts), torch.zeros(C, device=cuda), sc
 
 
-def reference_grads(net, A, data, gt, centers, targets, weights, points, vertex_w, w_inside, margin):
-    """torch fp32 autograd of the same losses on the same inputs; ROI pooling gathers at OUR arg-max positions."""
+def _ste(y, dtype):
+    """Round to a 16-bit format in the forward pass, identity in the backward pass (what storing an activation in bf16 / fp16 does)."""
+    return y + (y.to(dtype).float() - y).detach()
+
+
+def reference_grads(net, A, data, gt, centers, targets, weights, points, vertex_w, w_inside, margin, sim16):
+    """torch fp32 autograd of the same losses on the same inputs; ROI pooling gathers at OUR arg-max positions.
+    sim16=False: the reference graph in the reference's op order, pure fp32 (oracle/ref_network.py).
+    sim16=True:  the same mathematics in THIS implementation's op order (1x1 before the x8 up-sampling) with every stored activation
+    rounded to bf16 (trunk, heads) / fp16 (pose head) where our kernels round it — isolates kernel errors from precision effects."""
     P = {k: v.detach().clone().requires_grad_(True) for k, v in net.params.items()}
     C = net.num_classes
+    bf, hf = torch.bfloat16, torch.float16
+    r16 = (lambda y: _ste(y, bf)) if sim16 else (lambda y: y)
+    rh = (lambda y: _ste(y, hf)) if sim16 else (lambda y: y)
+    W = (lambda w: _ste(w, bf)) if sim16 else (lambda w: w)          # bf16 tensor-core copies of the weights
+    Wh = (lambda w: _ste(w, hf)) if sim16 else (lambda w: w)
     x = (data.float() - torch.tensor(MEANS, device=data.device)).permute(0, 3, 1, 2)
-    feats = R.trunk(P, x)
-    score, label, prob, vertex = R.heads(P, feats["conv4_3"], feats["conv5_3"], C)
+    if sim16:
+        x = r16(x)
+    feats = {}
+    for item in R.VGG_CFG:
+        if isinstance(item, str):
+            x = F.max_pool2d(x, 2)
+        else:
+            name = item[0]
+            x = r16(R.conv(x, W(P[f"{name}/weights"]), P[f"{name}/biases"]))
+            feats[name] = x
+    c4, c5 = feats["conv4_3"], feats["conv5_3"]
+    if sim16:
+        s5 = r16(R.conv(c5, W(P["score_conv5/weights"]), P["score_conv5/biases"]))
+        s4 = r16(R.conv(c4, W(P["score_conv4/weights"]), P["score_conv4/biases"]))
+        v5 = r16(R.conv(c5, W(P["score_conv5_vertex/weights"]), P["score_conv5_vertex/biases"], False))
+        v4 = r16(R.conv(c4, W(P["score_conv4_vertex/weights"]), P["score_conv4_vertex/biases"], False))
+        add_s, add_v = r16(s4 + R.deconv(s5, 4, 2)), r16(v4 + R.deconv(v5, 4, 2))
+        zs, zv = torch.zeros(C, device=data.device), torch.zeros(3 * C, device=data.device)
+        lr_s = r16(R.conv(add_s, W(P["score/weights"]), zs, False))
+        lr_v = r16(R.conv(add_v, W(P["vertex_pred/weights"]), zv, False))
+        score = torch.relu(R.deconv(lr_s, 16, 8) + P["score/biases"][None, :, None, None])
+        vertex = R.deconv(lr_v, 16, 8) + P["vertex_pred/biases"][None, :, None, None]
+        prob = F.softmax(score, 1)
+    else:
+        score, label, prob, vertex = R.heads(P, c4, c5, C)
     B = data.shape[0]
     g = gt.long()
     pg = prob.detach().gather(1, g.clamp(min=0)[:, None])[:, 0]
@@ -85,16 +121,15 @@ def reference_grads(net, A, data, gt, centers, targets, weights, points, vertex_
     rois = A["rois"]
     n = rois.shape[0]
 
-    def pool(feat, arg):                                  # feat NCHW -> [n,7,7,C] gather at the stored arg-max (image-relative NHWC index)
+    def pool(feat, arg):                                  # feat NCHW -> [n, 7*7*C] gather at the stored arg-max (image-relative NHWC index)
         f = feat.permute(0, 2, 3, 1).reshape(B, -1)
         idx = arg.reshape(n, -1).long()
         b = rois[:, 0].long()
-        out = f[b[:, None], idx.clamp(min=0)] * (idx >= 0)
-        return out
-    ps = pool(feats["conv5_3"], A["a5"]) + pool(feats["conv4_3"], A["a4"])
-    h6 = torch.relu(ps @ P["fc6/weights"] + P["fc6/biases"])
-    h7 = torch.relu(h6 @ P["fc7/weights"] + P["fc7/biases"])
-    th = torch.tanh(h7 @ P["fc8/weights"] + P["fc8/biases"])
+        return f[b[:, None], idx.clamp(min=0)] * (idx >= 0)
+    ps = rh(pool(c5, A["a5"]) + pool(c4, A["a4"]))
+    h6 = rh(torch.relu(ps @ Wh(P["fc6/weights"]) + P["fc6/biases"]))
+    h7 = rh(torch.relu(h6 @ Wh(P["fc7/weights"]) + P["fc7/biases"]))
+    th = torch.tanh(h7 @ Wh(P["fc8/weights"]) + P["fc8/biases"])
     mul = th * weights
     pred = mul / mul.pow(2).sum(1, keepdim=True).clamp(min=1e-12).sqrt()
     loss_pose = ad_loss_torch(pred, targets, weights, points, margin)
@@ -147,26 +182,30 @@ def test_training_step_matches_fp32_autograd(cuda):
     A["poses_weight"], A["poses_target"] = wt, tw
     grads = tr.backward(A, gt, centers)
     torch.cuda.synchronize()
-    P, ref = reference_grads(net, A, data, gt, centers, tw, wt, pts, vw_, wi, margin)
-    # forward parity of the training graph (bf16 trunk / heads, fp16 pose head)
-    assert rel_l2(A["score"].permute(0, 3, 1, 2), ref["score"]) < 3e-2
-    assert rel_l2(A["vertex_pred"].permute(0, 3, 1, 2), ref["vertex"]) < 3e-2
-    assert abs(A["cls_out"][0].item() - ref["loss_cls"]) < 3e-2 * max(1.0, abs(ref["loss_cls"]))
-    assert abs(vw_ * A["vtx_out"][0].item() - ref["loss_vertex"]) < 3e-2 * max(1.0, abs(ref["loss_vertex"]))
-    assert abs(A["loss_pose"].item() - ref["loss_pose"]) < 3e-2 * max(1e-3, abs(ref["loss_pose"]))
-    worst = {}
+    P, ref = reference_grads(net, A, data, gt, centers, tw, wt, pts, vw_, wi, margin, sim16=True)
+    Pf, reff = reference_grads(net, A, data, gt, centers, tw, wt, pts, vw_, wi, margin, sim16=False)
+    # forward parity of the training graph: tight against the 16-bit-rounded restatement, stated bf16 tolerance against pure fp32
+    assert rel_l2(A["score"].permute(0, 3, 1, 2), ref["score"]) < 5e-3
+    assert rel_l2(A["vertex_pred"].permute(0, 3, 1, 2), ref["vertex"]) < 5e-3
+    assert rel_l2(A["score"].permute(0, 3, 1, 2), reff["score"]) < 3e-2
+    assert rel_l2(A["vertex_pred"].permute(0, 3, 1, 2), reff["vertex"]) < 3e-2
+    for r_ in (ref, reff):
+        assert abs(A["cls_out"][0].item() - r_["loss_cls"]) < 3e-2 * max(1.0, abs(r_["loss_cls"]))
+        assert abs(vw_ * A["vtx_out"][0].item() - r_["loss_vertex"]) < 3e-2 * max(1.0, abs(r_["loss_vertex"]))
+        assert abs(A["loss_pose"].item() - r_["loss_pose"]) < 3e-2 * max(1e-3, abs(r_["loss_pose"]))
+    assert set(grads) == set(tr.master)
     for name, gr in grads.items():
         layer, kind = name.split("/")
-        want = P[f"{layer}/{'weights' if kind == 'w' else 'biases'}"].grad
+        key = f"{layer}/{'weights' if kind == 'w' else 'biases'}"
         got = to_tf_grad(tr, name, gr)
-        assert got.shape == want.shape, name
-        e = rel_l2(got, want)
-        worst[name] = e
-        print(f"grad {name:26s} rel-L2 {e:.3e}  |ref| {want.norm().item():.3e}")
-    assert set(grads) == set(tr.master)
-    for name, e in worst.items():
-        deep = name.startswith(("conv1", "conv2", "conv3"))
-        assert e < (6e-2 if deep else 3e-2), (name, e)
+        assert got.shape == P[key].grad.shape, name
+        e16, e32 = rel_l2(got, P[key].grad), rel_l2(got, Pf[key].grad)
+        print(f"grad {name:26s} rel-L2 vs 16-bit-rounded graph {e16:.3e}   vs pure fp32 graph {e32:.3e}   |ref| {P[key].grad.norm().item():.3e}")
+        # kernel correctness: same masks, same rounding points -> only the bf16 rounding of the propagated gradients is left
+        assert e16 < 3e-2, (name, e16)
+        # precision statement against the fp32 reference graph: ReLU / max-pool masks of a bf16 forward differ from the fp32 ones for
+        # near-tie activations, which compounds with depth; weight gradients of the first block are cancellation-heavy sums
+        assert e32 < (0.3 if layer in ("conv1_1", "conv1_2") else 0.1), (name, e32)
     # the update: accum = grad + wd * w (first step), w -= lr * accum; tensor-core copies refreshed
     before = {k: v.clone() for k, v in tr.master.items()}
     tr.update(grads)

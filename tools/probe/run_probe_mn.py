@@ -12,7 +12,7 @@ B = torch.randn(80, 64, device="cuda").to(torch.bfloat16)       # [pixel][Cin]
 out = torch.zeros(2, 9, 128, 64, device="cuda")
 rc = lib.umma_probe_mn(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), ctypes.c_void_p(out.data_ptr()))
 print("rc", rc)
-for var in range(2):
+for var in range(1):
     res = []
     for s in range(9):
         want = A[:64].float().t() @ B[s:s + 64].float()            # D[m][n] = sum_p A[p][m] B[p + s][n]
