@@ -15,7 +15,8 @@
 // pairs with row p of the other.  tcgen05.mma M = 128 (two 64-channel blocks, LBO apart), N <= 256, K = 16 pixels per
 // instruction, FP32 accumulation in TMEM.
 //
-//   work item  = (pixel range s, tap, Cin tile, Cout tile); items of one pixel range are adjacent in launch order so
+//   work item  = (pixel range s, tap group, Cin tile, Cout tile) — for Cin <= 128 up to four taps share one MMA as extra N blocks
+//                (N = 256 instead of 64: conv1_2's weight gradient 2.27 -> ms at batch 16); items of one pixel range are adjacent in launch order so
 //                that the 9 taps x tiles that re-read the same activations run together and hit in L2
 //   split-K    = the pixel ranges; partial [split][tap][Cout][Cin] fp32 in a workspace, fixed-order reduction
 //                (k_wgrad_finish) -> dW in the tensor-core weight layout [Cout][tap * Cin + ci] fp32
@@ -45,6 +46,7 @@ struct WgParams {
     int ktiles_per_split, splits;
     int n_tile, n_tiles, m_tiles;          // N tile (64 / 128 / 256), Cin / n_tile, ceil(Cout / 128)
     int f16;                               // operands are FP16 (the fully connected head) instead of BF16
+    int tg, tap_groups;                    // taps per work item (Cin <= 128: several taps share one MMA as extra N blocks), ceil(taps / tg)
 };
 
 // MN-major, 128-byte-swizzled operand: K rows of 128 B (64 channels), 8-row groups 1024 B apart (SBO), 64-channel
@@ -77,20 +79,22 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
     uint64_t* tfull = empty + kWgStages;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // item -> (split, tap, n tile, m tile); m fastest
+    // item -> (split, tap group, n tile, m tile); m fastest
     int item = blockIdx.x;
     const int mt = item % p.m_tiles; item /= p.m_tiles;
     const int nt = item % p.n_tiles; item /= p.n_tiles;
-    const int tap = item % p.taps;
-    const int split = item / p.taps;
+    const int tgi = item % p.tap_groups;
+    const int split = item / p.tap_groups;
     const int k_lo = split * p.ktiles_per_split, k_hi = min(k_lo + p.ktiles_per_split, p.ktiles);
     const int nk = k_hi - k_lo;
     const int m0 = mt * 128, n0 = nt * p.n_tile;
-    const int nb = p.n_tile / 64;                       // B blocks per stage
+    const int tap0 = tgi * p.tg, ntaps = min(p.tg, p.taps - tap0);
+    const int cb = p.n_tile / 64;                       // 64-channel B blocks per tap
+    const int nb = ntaps * cb;                          // B blocks per stage (<= 4): block j = (tap0 + j / cb, channels n0 + 64 (j % cb))
+    const int n_item = nb * 64;                         // UMMA N of this item
     const bool a2 = m0 + 64 < p.Cout;                   // second 64-channel block of dZ exists
-    const uint32_t tmem_cols = p.n_tile < 32 ? 32u : (uint32_t)p.n_tile;
+    const uint32_t tmem_cols = 256;
     const int pad = p.ksize / 2;
-    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
 
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -130,14 +134,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
                 mbar_arrive_expect_tx(&full[stage], tx);
                 tma_load_4d(st, &map_dz, &full[stage], m0, w0, h0, img);
                 if (a2) tma_load_4d(st + kWgBlk, &map_dz, &full[stage], m0 + 64, w0, h0, img);
-                for (int j = 0; j < nb; j++)
-                    tma_load_4d(st + (2 + j) * kWgBlk, &map_x, &full[stage], n0 + 64 * j, w0 + dx, h0 + dy, img);
+                for (int j = 0; j < nb; j++) {
+                    const int tap = tap0 + j / cb;
+                    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+                    tma_load_4d(st + (2 + j) * kWgBlk, &map_x, &full[stage], n0 + 64 * (j % cb), w0 + dx, h0 + dy, img);
+                }
                 if (++stage == kWgStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 5) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_mn(p.n_tile, p.f16);
+            const uint32_t idesc = make_idesc_mn(n_item, p.f16);
             int stage = 0;
             uint32_t phase = 0;
             for (int k = 0; k < nk; k++) {
@@ -159,17 +166,19 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
         tc_fence_after();
         const int co = m0 + warp * 32 + lane;
         const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float* dst = partial + (((size_t)split * p.taps + tap) * p.Cout + co) * p.Cin + n0;
-        for (int g = 0; g < p.n_tile / 32; g++) {
+        for (int g = 0; g < n_item / 32; g++) {
             uint32_t r[32];
             tmem_ld_32x32(t_addr + g * 32, r);
             tmem_ld_wait();
             if (co < p.Cout) {
+                const int j = g >> 1;                                   // B block of these 32 columns
+                const int tap = tap0 + j / cb, ci = n0 + 64 * (j % cb) + 32 * (g & 1);
+                float* dst = partial + (((size_t)split * p.taps + tap) * p.Cout + co) * p.Cin + ci;
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    *reinterpret_cast<float4*>(dst + g * 32 + j * 4) =
-                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                    __uint_as_float(r[4 * j + 3]));
+                for (int q = 0; q < 8; q++)
+                    *reinterpret_cast<float4*>(dst + q * 4) =
+                        make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                    __uint_as_float(r[4 * q + 3]));
             }
         }
         tc_fence_before();
@@ -215,7 +224,10 @@ k_wgrad_finish(const float* __restrict__ partial, int splits, int taps, int Cout
 // ---------------------------------------------------------------------------------------------
 constexpr int kEwThreads = 256;
 
-__device__ __forceinline__ void bias_accumulate(float* s_acc /*[C]*/, int c0, const float v[8])
+// Bias-gradient accumulation: the grid-stride step (gridDim.x * blockDim.x = 592 * 256) is a multiple of the channel-group
+// count for every C <= 4096 that is a multiple of 8 * 2^k, so a thread always meets the SAME 8 channels: it sums them in
+// registers and touches shared memory once at the end.
+__device__ __forceinline__ void bias_flush(float* s_acc /*[C]*/, int c0, const float v[8])
 {
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -232,10 +244,15 @@ k_relu_bwd(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict_
     __syncthreads();
     const int cg = C / 8;
     const size_t total = npix * cg;
-    // contiguous slab per CTA: fixed pixel -> CTA assignment (deterministic partial sums up to the smem atomics' order,
-    // which adds fp32 values of one CTA in a data-independent but unordered way; see k_bias_finish)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    const bool fixed = step % cg == 0;              // this thread's channel group never changes
+    float racc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) racc[j] = 0.f;
+    int c_fixed = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
         const int c0 = (int)(i % cg) * 8;
+        c_fixed = c0;
         const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g) + i);
         uint4 ov = gv;
         if (has_relu) {
@@ -248,14 +265,20 @@ k_relu_bwd(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict_
         }
         if (dz) reinterpret_cast<uint4*>(dz)[i] = ov;
         if (bias_partial) {
-            float v[8];
             const __nv_bfloat16* op = reinterpret_cast<const __nv_bfloat16*>(&ov);
+            if (fixed) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = __bfloat162float(op[j]);
-            bias_accumulate(s_acc, c0, v);
+                for (int j = 0; j < 8; j++) racc[j] += __bfloat162float(op[j]);
+            } else {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __bfloat162float(op[j]);
+                bias_flush(s_acc, c0, v);
+            }
         }
     }
     if (bias_partial) {
+        if (fixed) bias_flush(s_acc, c_fixed, racc);
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += kEwThreads) bias_partial[(size_t)blockIdx.x * C + c] = s_acc[c];
     }
@@ -303,7 +326,7 @@ k_maxpool_relu_bwd(const __nv_bfloat16* __restrict__ g /*[B,H/2,W/2,C]*/, const 
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(dz + offs[k]) = ov[k];
-        if (bias_partial) bias_accumulate(s_acc, gch * 8, bsum);
+        if (bias_partial) bias_flush(s_acc, gch * 8, bsum);
     }
     if (bias_partial) {
         __syncthreads();
@@ -311,17 +334,27 @@ k_maxpool_relu_bwd(const __nv_bfloat16* __restrict__ g /*[B,H/2,W/2,C]*/, const 
     }
 }
 
+// db[c] = scale * sum_k partial[k][c] (+ decay * b[c]); block = 32 channels x 8 row groups, groups combined in fixed order
 __global__ void __launch_bounds__(256)
 k_bias_finish(const float* __restrict__ partial, int nblocks, int C, float scale, const float* __restrict__ b, float decay,
               float* __restrict__ db)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float s[8][33];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float acc = 0.f;
-    for (int k = 0; k < nblocks; k++) acc += partial[(size_t)k * C + c];
-    acc *= scale;
-    if (b) acc = fmaf(decay, b[c], acc);     // weight decay is applied to the biases as well (network.py:184)
-    db[c] = acc;
+    if (c < C)
+        for (int k = grp; k < nblocks; k += 8) acc += partial[(size_t)k * C + c];
+    s[grp][cl] = acc;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += s[q][cl];
+        t *= scale;
+        if (b) t = fmaf(decay, b[c], t);     // weight decay is applied to the biases as well (network.py:184)
+        db[c] = t;
+    }
 }
 
 // out (bf16) = a (bf16) + b (bf16 or f32): gradient fan-in of conv4_3 / conv5_3 (score head + vertex head + RoiPoolGrad + trunk)
@@ -381,7 +414,10 @@ static int plan(int B, int H, int W, int Cin, int Cout, int ksize, WgParams* p)
     p->n_tile = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
     p->n_tiles = Cin / p->n_tile;
     p->m_tiles = (Cout + 127) / 128;
-    const int base = p->taps * p->n_tiles * p->m_tiles;
+    // Cin <= 128: N = Cin alone would issue small (N = 64 / 128) MMAs; several taps ride in one instruction as extra N blocks
+    p->tg = (p->n_tiles == 1 && p->n_tile < 256 && p->taps > 1) ? 256 / p->n_tile : 1;
+    p->tap_groups = (p->taps + p->tg - 1) / p->tg;
+    const int base = p->tap_groups * p->n_tiles * p->m_tiles;
     int want = (2 * kNumSMs + base - 1) / base;          // ~two waves of work items
     if (want < 1) want = 1;
     if (want > p->ktiles) want = p->ktiles;
@@ -442,7 +478,7 @@ static int wgrad_impl(const void* x_bf16, const void* dz_bf16, int B, int H, int
     if (rc) return rc;
     PCNN_SMEM_OPTIN(k_wgrad_tc, kWgSmem, "wgrad_tc");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long items = (long long)p.splits * p.taps * p.n_tiles * p.m_tiles;
+    const long long items = (long long)p.splits * p.tap_groups * p.n_tiles * p.m_tiles;
     PCNN_REQUIRE(items < 0x7fffffffLL, "conv_wgrad: too many work items");
     k_wgrad_tc<<<(unsigned)items, kWgThreads, kWgSmem, st>>>(mx, mz, (float*)workspace, p);
     rc = check_launch("wgrad_tc");
@@ -464,7 +500,7 @@ extern "C" int pcnn_relu_bwd_bf16(const void* g_bf16, const void* y_bf16, size_t
     cudaStream_t st = (cudaStream_t)stream;
     k_relu_bwd<<<grid, kEwThreads, db ? sizeof(float) * C : 0, st>>>((const __nv_bfloat16*)g_bf16, (const __nv_bfloat16*)y_bf16, npix, C, has_relu,
                                                                      (__nv_bfloat16*)dz_bf16, db ? (float*)bias_ws : nullptr);
-    if (db) k_bias_finish<<<(C + 255) / 256, 256, 0, st>>>((const float*)bias_ws, grid, C, scale, b, decay, db);
+    if (db) k_bias_finish<<<(C + 31) / 32, 256, 0, st>>>((const float*)bias_ws, grid, C, scale, b, decay, db);
     return check_launch("relu_bwd");
 }
 
@@ -479,7 +515,7 @@ extern "C" int pcnn_maxpool_relu_bwd_bf16(const void* g_bf16, const void* y_bf16
     cudaStream_t st = (cudaStream_t)stream;
     k_maxpool_relu_bwd<<<grid, kEwThreads, db ? sizeof(float) * C : 0, st>>>((const __nv_bfloat16*)g_bf16, (const __nv_bfloat16*)y_bf16, B, H, W, C,
                                                                              (__nv_bfloat16*)dz_bf16, db ? (float*)bias_ws : nullptr);
-    if (db) k_bias_finish<<<(C + 255) / 256, 256, 0, st>>>((const float*)bias_ws, grid, C, scale, b, decay, db);
+    if (db) k_bias_finish<<<(C + 31) / 32, 256, 0, st>>>((const float*)bias_ws, grid, C, scale, b, decay, db);
     return check_launch("maxpool_relu_bwd");
 }
 

@@ -283,7 +283,7 @@ class Trainer:
         d_sc = torch.empty((B, h, w, 64), dtype=torch.bfloat16, device=dev)
         d_vt = torch.empty((B, h, w, 128), dtype=torch.bfloat16, device=dev)
         dbias = torch.empty((4 * C,), dtype=torch.float32, device=dev)
-        ws = workspace("up8_bwd", 4 * B * h * 4 * C, dev)
+        ws = workspace("up8_bwd", 4 * B * h * ((w + 15) // 16) * 4 * C, dev)
         check(lib().pcnn_up8_heads_bwd(ptr(A["prob_normalized"]), ptr(A["score"]), ptr(gt_label_2d), ptr(A["cls_out"]), f32(1.0),
                                        f32(net.threshold_label), ptr(A["vertex_pred"]), ptr(centers), ptr(A["vtx_out"]), f32(self.vertex_w),
                                        f32(self.w_inside), f32(1.0), B, h, w, C, 64, 128, ptr(d_sc), ptr(d_vt), ptr(dbias), ptr(ws),
@@ -327,13 +327,10 @@ class Trainer:
                 dz, db = bw.relu_bwd(g, y, True, want_bias=True)
             self._emit(grads, name + "/b", db)
             if name == "conv1_1":
-                dW = torch.empty((64, 27), dtype=torch.float32, device=dev)
-                wsz = 4 * 148 * 4 * 64 * 27
-                wsb = workspace("conv1_wgrad", wsz, dev)
-                mean = (ctypes.c_float * 3)(*PIXEL_MEANS)
-                check(lib().pcnn_conv1_wgrad(ptr(data), mean, ptr(dz), B, H, W, f32(1.0), ptr(None), f32(0.0), ptr(dW), ptr(wsb),
-                                             ctypes.c_size_t(wsb.numel()), stream()))
-                self._emit(grads, name + "/w", dW)
+                # Cin = 3: the weight gradient is the 1x1 tensor-core wgrad on the im2col view of the image (K = tap * 3 + c, the same
+                # bf16 (pixel - mean) values the forward MMA consumed); a CUDA-core kernel (pcnn_conv1_wgrad) took 2.6 ms at batch 16
+                cols = conv.im2col_c3(data, PIXEL_MEANS)                                       # [B,H,W,64] bf16, 27 columns used
+                self._emit(grads, name + "/w", bw.conv_wgrad(cols, dz, 1)[:, :27].contiguous())
                 break
             prev = CONV_NAMES[CONV_NAMES.index(name) - 1]
             x_in = A.get(prev + "/pool", A[prev])
