@@ -53,7 +53,7 @@ class Trainer:
         self.net, self.lr, self.mu, self.wd = net, float(lr), float(momentum), float(weight_decay)
         self.vertex_w, self.w_inside, self.margin, self.world = float(vertex_w), float(vertex_w_inside), float(margin), int(world)
         self.C = net.num_classes
-        self.pose_loss_scale = 4096.0            # loss scale of the fp16 pose-head backward (see backward())
+        self.pose_loss_scale = 1.0               # last dynamic loss scale of the fp16 pose-head backward (see backward())
         self.comm = torch.cuda.Stream(device=net.device) if world > 1 else None
         P, dev = net.params, net.device
         C = self.C
@@ -259,11 +259,19 @@ class Trainer:
         A["loss_pose"] = A["loss_pose_raw"] * pose_scale
         # ---- pose head
         # The head's backward GEMMs run on FP16 operands like its forward.  The pose-loss gradients are tiny (a mean over rows x points:
-        # 1e-6 .. 1e-4 per element, below fp16's normal range), so the chain is LOSS-SCALED by S = 2^12 where it enters fp16 and un-scaled
+        # 1e-6 .. 1e-4 per element, below fp16's normal range), so the chain is LOSS-SCALED by a dynamic power of two S where it enters fp16 and un-scaled
         # where it leaves (weight gradients, bias sums, the RoiPool gradient); conversions saturate at +-65504.
-        S = self.pose_loss_scale
         D = 4 * C
         dpre = torch.empty((rows, 128), dtype=torch.float16, device=dev)
+        check(lib().pcnn_pose_chain_bwd(ptr(A["pose_diff"]), ptr(A["poses_tanh"]), ptr(A["poses_weight"]), rows, D, f32(pose_scale), ptr(dpre), 128,
+                                        stream()))
+        # dynamic loss scale: a power of two that puts the largest element of the chain's entry point at ~2^11 (one host read; the
+        # un-scaled pass above is only used for its maximum, which fp16 represents well enough even when the small elements underflow)
+        amax = float(dpre.float().abs().max().item())
+        if self.world > 1:
+            t = torch.tensor([amax], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); amax = float(t.item())
+        S = 2.0 ** max(0, min(24, int(torch.floor(torch.log2(torch.tensor(2048.0 / max(amax, 1e-30)))).item()))) if amax > 0 else 1.0
+        self.pose_loss_scale = S
         check(lib().pcnn_pose_chain_bwd(ptr(A["pose_diff"]), ptr(A["poses_tanh"]), ptr(A["poses_weight"]), rows, D, f32(pose_scale * S), ptr(dpre), 128,
                                         stream()))
         self._emit(grads, "fc8/w", self._fc_wgrad(A["fc7"], dpre, 1.0 / S))
