@@ -516,7 +516,7 @@ def run_full(args, rank, world, local, input_format="COLOR"):
                     background_calibration="score/biases[0] += %.4g so that ~75%% of pixels are background (YCB-like fill); "
                                            "un-calibrated random init labels ~100%% of pixels foreground" % bg_shift),
         clocks=clocks, gpu_launches=(LAUNCHES_FULL + (14 if input_format == "RGBD" else 0)) * args.steps,
-        roofline=dict(bound="tensor", achieved=tf * ntrunks, peak=burst, unit="TFLOP/s", frac=tf * ntrunks / burst, frac_sustained=tf * ntrunks / sust,
+        roofline=dict(bound="tensor", achieved=tf, peak=burst, unit="TFLOP/s", frac=tf / burst, frac_sustained=tf / sust,
                       peak_sustained=sust, traffic=(traffic or {}).get("trunk_dram_bytes_per_launch_group") if (traffic or {}).get("batch") == Bl else None,
                       peak_source=peaks["source"] + ": burst cuBLAS bf16 (kernel group timed alone); frac_sustained = vs the sustained figure",
                       kernel="conv trunk: k_conv1_tc, k_conv_row2 x3, k_conv_tc<256> x9, 1 max-pool (3 pools fused)",

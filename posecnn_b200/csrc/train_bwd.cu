@@ -154,12 +154,18 @@ k_up8_bwd(const float* __restrict__ prob, const float* __restrict__ score, const
                         const float* pp = prob + p * C;
                         const float* sp = score + p * C;
                         if (CT) {
+                            // C even: a pixel's C floats are 8-byte aligned -> 64-bit loads
+                            const float2* pp2 = reinterpret_cast<const float2*>(pp);
+                            const float2* sp2 = reinterpret_cast<const float2*>(sp);
 #pragma unroll
-                            for (int c = 0; c < (CT ? CT : 1); c++) {
-                                float d = 0.f;
-                                if (__ldg(sp + c) > 0.f) d = s_cls * (__ldg(pp + c) - (c == g ? 1.f : 0.f));
-                                acc[c] = fmaf(wy, d, acc[c]);
-                                if (own && d != 0.f) atomicAdd(&s_db[c], d);
+                            for (int c2 = 0; c2 < (CT ? CT / 2 : 1); c2++) {
+                                const float2 sv = __ldg(sp2 + c2), pv = __ldg(pp2 + c2);
+                                const float d0 = sv.x > 0.f ? s_cls * (pv.x - (2 * c2 == g ? 1.f : 0.f)) : 0.f;
+                                const float d1 = sv.y > 0.f ? s_cls * (pv.y - (2 * c2 + 1 == g ? 1.f : 0.f)) : 0.f;
+                                acc[2 * c2] = fmaf(wy, d0, acc[2 * c2]);
+                                acc[2 * c2 + 1] = fmaf(wy, d1, acc[2 * c2 + 1]);
+                                if (own && d0 != 0.f) atomicAdd(&s_db[2 * c2], d0);
+                                if (own && d1 != 0.f) atomicAdd(&s_db[2 * c2 + 1], d1);
                             }
                         } else {
                             for (int c = 0; c < C; c++) {
@@ -219,16 +225,26 @@ k_up8_bwd(const float* __restrict__ prob, const float* __restrict__ score, const
     for (int i = t; i < No; i += blockDim.x) dbias_partial[cta * No + i] = s_db[i];
 }
 
+// out[i] = scale * sum_k partial[k][i] (+ decay * p[i]); block = 32 columns x 8 row groups, groups combined in fixed order
 __global__ void __launch_bounds__(256)
 k_sum_partials(const float* __restrict__ partial, int nparts, int n, float scale, const float* __restrict__ p, float decay, float* __restrict__ out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    __shared__ float s[8][33];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cl;
     float acc = 0.f;
-    for (int k = 0; k < nparts; k++) acc += partial[(size_t)k * n + i];
-    acc *= scale;
-    if (p) acc = fmaf(decay, p[i], acc);
-    out[i] = acc;
+    if (i < n)
+        for (int k = grp; k < nparts; k += 8) acc += partial[(size_t)k * n + i];
+    s[grp][cl] = acc;
+    __syncthreads();
+    if (grp == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += s[q][cl];
+        t *= scale;
+        if (p) t = fmaf(decay, p[i], t);
+        out[i] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,7 +434,7 @@ extern "C" int pcnn_up8_heads_bwd(const float* prob, const float* score, const i
                                                  upstream_vertex, w_inside, sigma * sigma, h, w, C, Cs, Cv, (__nv_bfloat16*)d_sc_bf16,
                                                  (__nv_bfloat16*)d_vt_bf16, (float*)workspace);
     }
-    k_sum_partials<<<(4 * C + 255) / 256, 256, 0, st>>>((const float*)workspace, B * h * chunks, 4 * C, 1.f, nullptr, 0.f, dbias);
+    k_sum_partials<<<(4 * C + 31) / 32, 256, 0, st>>>((const float*)workspace, B * h * chunks, 4 * C, 1.f, nullptr, 0.f, dbias);
     return check_launch("up8_heads_bwd");
 }
 
@@ -467,6 +483,6 @@ extern "C" int pcnn_conv1_wgrad(const void* img_u8, const float* mean3_host, con
     if (mean3_host) { m0 = mean3_host[0]; m1 = mean3_host[1]; m2 = mean3_host[2]; }
     cudaStream_t st = (cudaStream_t)stream;
     k_conv1_wgrad<<<grid, 256, 0, st>>>((const unsigned char*)img_u8, (const __nv_bfloat16*)dz_bf16, B, H, W, m0, m1, m2, (float*)workspace);
-    k_sum_partials<<<(64 * 27 + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, 64 * 27, scale, w, decay, dW);
+    k_sum_partials<<<(64 * 27 + 31) / 32, 256, 0, st>>>((const float*)workspace, grid, 64 * 27, scale, w, decay, dW);
     return check_launch("conv1_wgrad");
 }

@@ -123,6 +123,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = (uint32_t)((a2 ? 2 : 1) + nb) * kWgBlk;
+            int bdx[kWgMaxNB], bdy[kWgMaxNB], bch[kWgMaxNB];       // per B block: tap offset and channel origin (loop invariant)
+#pragma unroll
+            for (int j = 0; j < kWgMaxNB; j++) {
+                const int tap = tap0 + j / cb;
+                bdy[j] = tap / p.ksize - pad; bdx[j] = tap % p.ksize - pad; bch[j] = n0 + 64 * (j % cb);
+            }
             for (int k = 0; k < nk; k++) {
                 int kt = k_lo + k;
                 const int tw = kt % p.tiles_w; kt /= p.tiles_w;
@@ -134,11 +140,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
                 mbar_arrive_expect_tx(&full[stage], tx);
                 tma_load_4d(st, &map_dz, &full[stage], m0, w0, h0, img);
                 if (a2) tma_load_4d(st + kWgBlk, &map_dz, &full[stage], m0 + 64, w0, h0, img);
-                for (int j = 0; j < nb; j++) {
-                    const int tap = tap0 + j / cb;
-                    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
-                    tma_load_4d(st + (2 + j) * kWgBlk, &map_x, &full[stage], n0 + 64 * (j % cb), w0 + dx, h0 + dy, img);
-                }
+#pragma unroll
+                for (int j = 0; j < kWgMaxNB; j++)
+                    if (j < nb) tma_load_4d(st + (2 + j) * kWgBlk, &map_x, &full[stage], bch[j], w0 + bdx[j], h0 + bdy[j], img);
                 if (++stage == kWgStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -418,7 +422,7 @@ static int plan(int B, int H, int W, int Cin, int Cout, int ksize, WgParams* p)
     p->tg = (p->n_tiles == 1 && p->n_tile < 256 && p->taps > 1) ? 256 / p->n_tile : 1;
     p->tap_groups = (p->taps + p->tg - 1) / p->tg;
     const int base = p->tap_groups * p->n_tiles * p->m_tiles;
-    int want = (2 * kNumSMs + base - 1) / base;          // ~two waves of work items
+    int want = (2 * kNumSMs) / base;                     // just under two full waves of work items (no third, nearly empty wave)
     if (want < 1) want = 1;
     if (want > p->ktiles) want = p->ktiles;
     p->ktiles_per_split = (p->ktiles + want - 1) / want;

@@ -108,3 +108,45 @@ def test_conv1_wgrad_cuda_cores(cuda):
     m = (ctypes.c_float * 3)(*mean)
     check(lib().pcnn_conv1_wgrad(ptr(img), m, ptr(dz), B, H, W, f32(1.0), ptr(None), f32(0.0), ptr(got), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
     assert rel_l2(got, want) < 1e-5
+
+
+def test_fc_dgrad_wgrad_and_pose_chain(cuda):
+    """Fully connected backward GEMMs (fp16 operands) and the pose-loss chain against torch on the same operands."""
+    import ctypes
+    from posecnn_b200 import pose_head
+    from posecnn_b200._lib import check, f32, lib, ptr, stream, workspace
+    g = torch.Generator().manual_seed(11)
+    rows, Kin, Nout = 45, 4096, 256
+    x = torch.relu(torch.randn(rows, Kin, generator=g)).to(torch.float16).to(cuda)          # stored output of the layer below (ReLU)
+    w = (torch.randn(Kin, Nout, generator=g) / Kin ** 0.5).to(cuda)                           # TF layout [in, out]
+    dy = (torch.randn(rows, Nout, generator=g) * 0.3).to(torch.float16).to(cuda)
+    w_tc = pose_head.fc_weights_to_tc(w)                                                       # [out][in] fp16
+    w_t = torch.empty((Kin, Nout), dtype=torch.float16, device=cuda)
+    check(lib().pcnn_transpose16(ptr(w_tc), Nout, Kin, ptr(w_t), stream()))
+    assert torch.equal(w_t, w_tc.t().contiguous())
+    # input gradient with the ReLU mask of the layer below
+    out = torch.empty((rows, Kin), dtype=torch.float16, device=cuda)
+    nbytes = ctypes.c_size_t(0)
+    check(lib().pcnn_fc_workspace_bytes(rows, Kin, Nout, ctypes.byref(nbytes)))
+    ws = workspace("fc", nbytes.value, cuda)
+    check(lib().pcnn_fc_dgrad_f16_tc(ptr(dy), ptr(w_t), rows, Kin, Nout, ptr(x), ptr(out), Kin, ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    want = (dy.float() @ w_tc.float()) * (x.float() > 0)
+    assert rel_l2(out.float(), want) < 2e-3
+    # weight gradient [out][in] with a scale
+    dw = torch.empty((Nout, Kin), dtype=torch.float32, device=cuda)
+    check(lib().pcnn_conv_wgrad_workspace_bytes(1, 1, rows, Kin, Nout, 1, ctypes.byref(nbytes)))
+    ws2 = workspace("wgrad", nbytes.value, cuda)
+    check(lib().pcnn_fc_wgrad_f16_tc(ptr(x), ptr(dy), rows, Kin, Nout, f32(0.25), ptr(None), f32(0.0), ptr(dw), ptr(ws2), ctypes.c_size_t(ws2.numel()), stream()))
+    assert rel_l2(dw, 0.25 * dy.float().t() @ x.float()) < 1e-4
+    # pose chain: d pre-activation of fc8 from d loss / d poses_pred, poses_pred = l2_normalize(tanh(pre) * weight)
+    N, D = 19, 24
+    pre = torch.randn(N, D, generator=g).to(cuda).requires_grad_(True)
+    wt = torch.zeros(N, D); wt[:, 4:8] = 1.0; wt[3] = 0.0; wt = wt.to(cuda)                   # one class active; one all-zero row (clamped norm)
+    gup = torch.randn(N, D, generator=g).to(cuda)
+    th = torch.tanh(pre)
+    mul = th * wt
+    pred = mul / mul.pow(2).sum(1, keepdim=True).clamp(min=1e-12).sqrt()
+    (pred * gup).sum().backward()
+    dpre = torch.empty((N, 128), dtype=torch.float16, device=cuda)
+    check(lib().pcnn_pose_chain_bwd(ptr(gup), ptr(th.detach().contiguous()), ptr(wt), N, D, f32(1.0), ptr(dpre), 128, stream()))
+    assert rel_l2(dpre[:, :D].float(), pre.grad) < 2e-3 and float(dpre[:, D:].float().abs().max()) == 0.0
