@@ -208,11 +208,14 @@ def test_training_step_matches_fp32_autograd(cuda):
         # kernel correctness: same masks, same rounding points -> only the 16-bit rounding of the PROPAGATED gradients is left (the
         # reference keeps them in fp32); weight / bias gradients are cancellation-heavy sums, so that rounding noise shows amplified:
         # measured 0.1-0.7e-2 on the heads, 2e-2 -> 4e-2 down the trunk, 7e-2 / 1.2e-1 on the conv1_2 / conv1_1 weights
-        lim = 0.2 if name == "conv1_1/w" else (0.1 if layer in ("conv1_1", "conv1_2") else 6e-2)
+        # pose head: d loss / d poses_tanh after l2_normalize is what is left when the radial component of Averagedistance's gradient is
+        # removed — a cancellation residual, so the 1e-3 relative differences of an fp16 forward show up as 1e-2 .. 1e-1 in fc6 / fc7 / fc8
+        # gradients (|ref| 1e-6 .. 1e-2); the GEMMs themselves are checked to 2e-3 / 1e-4 in tests/test_backward_gpu.py
+        lim = 0.2 if name == "conv1_1/w" else (0.15 if layer in ("conv1_1", "conv1_2", "fc6", "fc7", "fc8") else 6e-2)
         assert e16 < lim, (name, e16)
         # precision statement against the fp32 reference graph: ReLU / max-pool masks of a bf16 forward differ from the fp32 ones for
         # near-tie activations, which compounds with depth; weight gradients of the first block are cancellation-heavy sums
-        assert e32 < (0.3 if layer in ("conv1_1", "conv1_2") else 0.1), (name, e32)
+        assert e32 < (0.3 if layer in ("conv1_1", "conv1_2") else (0.15 if layer in ("fc6", "fc7", "fc8") else 0.1)), (name, e32)
     # the update: accum = grad + wd * w (first step), w -= lr * accum; tensor-core copies refreshed
     before = {k: v.clone() for k, v in tr.master.items()}
     tr.update(grads)
