@@ -32,6 +32,7 @@ METRIC_FULL = "frames/sec on 640x480 RGB, 21 classes, batch 32 (VGG16 + Hough + 
 # kernels of one step's CUDA graph: trunk 14 (conv1 fused, 12 conv of which 3 with fused pool, pool4) + 1x1 heads 4 +
 # lowres_heads + up8_heads + hough 7 + roi_pool_pair + 3 x (fc_tc + fc_finish) + nms_pose
 LAUNCHES_FULL = 14 + 4 + 2 + 7 + 1 + 6 + 1
+TRAIN_OWN_LAUNCHES_PER_STEP = 209   # own kernels of one training step (ncu launch list); the run counts them live with CUPTI when it can
 
 
 def measured_peaks():
@@ -109,6 +110,42 @@ def max_over_ranks(x, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
     return float(x)
+
+
+def count_own_launches(fn):
+    """Kernels of THIS repo launched by one call of fn(), counted with CUPTI through torch.profiler (every kernel on the device is
+    seen, also those launched through the C ABI); ATen / NCCL / memcpy / memset activities are not counted.  None if the profiler
+    is unavailable."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        own = other = 0
+        per = {}
+        for ev in prof.events():
+            if ev.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            n = ev.name
+            if n.startswith(("Memcpy", "Memset")) or "nccl" in n.lower():
+                continue
+            if "at::" in n or "cub::" in n or n.startswith(("void at", "nvjet", "cutlass", "sm90", "sm100")):
+                other += 1
+                key = "library (ATen)"
+            else:
+                own += 1
+                key = n.split("(")[0].replace("void ", "")[:48]
+            a = per.setdefault(key, [0.0, 0])
+            a[0] += float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0)) / 1e3
+            a[1] += 1
+        top = sorted(per.items(), key=lambda kv: -kv[1][0])[:16]
+        return dict(own=own, library=other, kernel_ms_top={k: [round(v[0], 3), v[1]] for k, v in top},
+                    kernel_ms_total=round(sum(v[0] for v in per.values()), 3)) if own + other > 0 else None
+    except Exception as e:  # pragma: no cover
+        print("launch count via torch.profiler failed: %s" % e, file=sys.stderr)
+        return None
 
 
 def profile_json(name):
@@ -698,6 +735,7 @@ def run_train(args, rank, world, local):
         h_loss.copy_(o["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
     dt = max_over_ranks((time.perf_counter() - t0) / k, world)
+    launches = count_own_launches(lambda: step(data, gtl))
     peaks = measured_peaks()
     flop = 3.0 * VGG_FLOP_PER_FRAME * Bl                      # forward + input-gradient + weight-gradient GEMMs of the trunk
     tf = flop / (ms_step * 1e-3) / 1e12
@@ -712,7 +750,8 @@ def run_train(args, rank, world, local):
                     parallelism="image shards x%d, global loss normalisers, per-tensor NCCL all-reduce (SUM) of the gradients on a side stream" % world,
                     l2="no flush: %.1f GB of saved activations per step (>> 126 MB L2)" % (0.31 * Bl), rois_rows=int(out["num_rois"].item()),
                     losses=dict(cls=float(out["loss_cls"].item()), vertex=float(out["loss_vertex"].item()), pose=float(out["loss_pose"].item()))),
-        clocks=clocks, gpu_launches=None,
+        clocks=clocks, gpu_launches=(launches["own"] if launches else TRAIN_OWN_LAUNCHES_PER_STEP) * args.steps,
+        launches_per_step=launches or dict(own=TRAIN_OWN_LAUNCHES_PER_STEP, source="ncu launch list profiles/r02_train_b16_launches.csv"),
         roofline=dict(bound="tensor", achieved=tf, peak=sust, unit="TFLOP/s", frac=tf / sust, traffic=None, peak_source=peaks["source"] + " (sustained: a kernel "
                       "group inside a long step)", kernel="trunk GEMMs: 13 forward convolutions + 12 dgrad (k_conv_tc / k_conv_row2) + 12 wgrad (k_wgrad_tc)",
                       note="achieved = 3 x 187.918 GFLOP/frame x this rank's frames / WHOLE step time (heads, losses, pose head, update included)"),

@@ -238,6 +238,13 @@ int pcnn_up8_heads_bwd(const float* prob, const float* score, const int32_t* gt,
                        float threshold, const float* vertex_pred, const float* centers, const float* vertex_loss_out,
                        float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C, int Cs, int Cv,
                        void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+/* the same with vertex_pred == NULL: the labelled pixels' vertex values are formed from the low-resolution head tensor
+ * `lowres` [B,h,w,4C] + bias_vertex [3C] (no dense vertex_pred in the training step; C = 22) */
+int pcnn_up8_heads_bwd_ex(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
+                          float threshold, const float* vertex_pred, const float* lowres, const float* bias_vertex, const float* centers,
+                          const float* vertex_loss_out, float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C,
+                          int Cs, int Cv, void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes,
+                          void* stream);
 int pcnn_pose_chain_bwd(const float* bottom_diff, const float* poses_tanh, const float* poses_weight, int N, int D, float upstream,
                         void* dpre_f16, int ld, void* stream);
 int pcnn_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float lr, float mu, float wd, float gscale, void* copy16,
@@ -355,6 +362,11 @@ int pcnn_smooth_l1_vertex_fwd(const float* pred, const float* targets, const flo
 int pcnn_vertex_loss_fused_fwd(const float* pred, const int32_t* label, const float* centers, int B, int H, int W, int C,
                                float w_inside, float sigma, float* loss_out, float upstream, float* grad_pred,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* the same loss with the vertex head given as the 1/8-resolution head tensor `lowres` [B,H/8,W/8,4C] + the vertex_pred bias [3C]
+ * (values formed on demand with k_up8_heads' operation sequence: bit-identical to the dense tensor) */
+int pcnn_vertex_loss_fused_lowres_fwd(const float* lowres, const float* bias_vertex, const int32_t* label, const float* centers, int B,
+                                      int H, int W, int C, float w_inside, float sigma, float* loss_out, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

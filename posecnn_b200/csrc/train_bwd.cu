@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "heads_common.cuh"
@@ -25,19 +26,42 @@ namespace pcnn {
 // ---------------------------------------------------------------------------------------------
 // add[b,h,w,c] = a4[b,h,w,c] + sum_i a5[b, i, j, c] * W4[h - 2 i + 1] * W4[w - 2 j + 1]   (conv2d_transpose 4x4 / 2, SAME)
 // ---------------------------------------------------------------------------------------------
+// thread = (pixel, group of 8 channels): 128-bit loads / stores (C % 8 == 0)
+__device__ __forceinline__ void acc8(float acc[8], float wgt, const uint4& v)
+{
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float2 f = __bfloat1622float2(p[q]);
+        acc[2 * q] = fmaf(wgt, f.x, acc[2 * q]);
+        acc[2 * q + 1] = fmaf(wgt, f.y, acc[2 * q + 1]);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float acc[8])
+{
+    uint4 o;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; q++) p[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+    return o;
+}
+
 __global__ void __launch_bounds__(256)
 k_add_up2(const __nv_bfloat16* __restrict__ a4, const __nv_bfloat16* __restrict__ a5, int B, int h, int w, int C,
           __nv_bfloat16* __restrict__ out)
 {
-    const int h5 = h / 2, w5 = w / 2;
-    const size_t total = (size_t)B * h * w * C;
+    const int h5 = h / 2, w5 = w / 2, cg = C / 8;
+    const size_t total = (size_t)B * h * w * cg;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t r = i / C;
+        const int g = (int)(i % cg);
+        size_t r = i / cg;
         const int x = (int)(r % w); r /= w;
         const int y = (int)(r % h);
         const size_t n = r / h;
-        float acc = __bfloat162float(a4[i]);
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0.f;
+        acc8(acc, 1.f, __ldg(reinterpret_cast<const uint4*>(a4) + i));
         // contributing source rows: ky = y - 2 iy + 1 in [0, 4)
         for (int iy = (y - 2) / 2; iy <= (y + 1) / 2; iy++) {
             const int ky = y - 2 * iy + 1;
@@ -45,10 +69,10 @@ k_add_up2(const __nv_bfloat16* __restrict__ a4, const __nv_bfloat16* __restrict_
             for (int ix = (x - 2) / 2; ix <= (x + 1) / 2; ix++) {
                 const int kx = x - 2 * ix + 1;
                 if (ix < 0 || ix >= w5 || kx < 0 || kx >= 4) continue;
-                acc = fmaf(deconv_w(ky, 4) * deconv_w(kx, 4), __bfloat162float(a5[((n * h5 + iy) * w5 + ix) * C + c]), acc);
+                acc8(acc, deconv_w(ky, 4) * deconv_w(kx, 4), __ldg(reinterpret_cast<const uint4*>(a5 + ((n * h5 + iy) * w5 + ix) * C) + g));
             }
         }
-        out[i] = __float2bfloat16_rn(acc);
+        reinterpret_cast<uint4*>(out)[i] = pack8(acc);
     }
 }
 
@@ -57,27 +81,34 @@ __global__ void __launch_bounds__(256)
 k_up2_bwd(const __nv_bfloat16* __restrict__ dadd /*[B,h,w,C]*/, const __nv_bfloat16* __restrict__ y5 /*[B,h/2,w/2,C] or null*/, int B,
           int h, int w, int C, __nv_bfloat16* __restrict__ d5)
 {
-    const int h5 = h / 2, w5 = w / 2;
-    const size_t total = (size_t)B * h5 * w5 * C;
+    const int h5 = h / 2, w5 = w / 2, cg = C / 8;
+    const size_t total = (size_t)B * h5 * w5 * cg;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        size_t r = i / C;
+        const int g = (int)(i % cg);
+        size_t r = i / cg;
         const int ix = (int)(r % w5); r /= w5;
         const int iy = (int)(r % h5);
         const size_t n = r / h5;
-        float acc = 0.f;
-        if (!y5 || __bfloat162float(y5[i]) > 0.f) {
-            for (int ky = 0; ky < 4; ky++) {
-                const int y = 2 * iy - 1 + ky;
-                if (y < 0 || y >= h) continue;
-                for (int kx = 0; kx < 4; kx++) {
-                    const int x = 2 * ix - 1 + kx;
-                    if (x < 0 || x >= w) continue;
-                    acc = fmaf(deconv_w(ky, 4) * deconv_w(kx, 4), __bfloat162float(dadd[((n * h + y) * w + x) * C + c]), acc);
-                }
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0.f;
+        for (int ky = 0; ky < 4; ky++) {
+            const int y = 2 * iy - 1 + ky;
+            if (y < 0 || y >= h) continue;
+            for (int kx = 0; kx < 4; kx++) {
+                const int x = 2 * ix - 1 + kx;
+                if (x < 0 || x >= w) continue;
+                acc8(acc, deconv_w(ky, 4) * deconv_w(kx, 4), __ldg(reinterpret_cast<const uint4*>(dadd + ((n * h + y) * w + x) * C) + g));
             }
         }
-        d5[i] = __float2bfloat16_rn(acc);
+        if (y5) {
+            const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y5) + i);
+            const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(&yv);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (!(__bfloat162float(yp[q]) > 0.f)) acc[q] = 0.f;
+        }
+        reinterpret_cast<uint4*>(d5)[i] = pack8(acc);
     }
 }
 
@@ -223,6 +254,144 @@ k_up8_bwd(const float* __restrict__ prob, const float* __restrict__ score, const
     }
     const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     for (int i = t; i < No; i += blockDim.x) dbias_partial[cta * No + i] = s_db[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_up8_bwd_strip: the same gradient, organised so that every byte of prob / score is read (nearly) once and every load is
+// coalesced.  CTA = (image, strip of kSC low-resolution columns = 8 kSC + 8 output columns incl. the halo, band of `rb`
+// low-resolution rows).  Thread = (output column, channel PAIR): the CTA's threads read one contiguous run of
+// kCols * C floats per output row of prob and of score (64-bit loads).  The thread walks DOWN the band's 8 rb + 8 output
+// rows; a pixel row contributes to exactly two low-resolution rows (taps ky and ky + 8), so two running vertical sums per
+// channel live in registers and the finished one is handed to the horizontal pass every 8 rows (same fmaf order as
+// k_up8_bwd: the two kernels agree bit for bit on d_sc / d_vt).  The three vertex channels of a labelled pixel go to a
+// per-column shared-memory accumulator owned by thread (column, k).  Bias gradients: per-thread registers (fixed channel
+// pair) / per-column shared-memory cells, reduced over the columns in a fixed order (no atomics: run-to-run deterministic).
+// Redundant reads: (8 kSC + 8) / (8 kSC) x (8 rb + 8) / (8 rb) = 1.25 x 1.07 at kSC = 4, rb = 16 (k_up8_bwd: 2 x 1.06, stride-88-B loads).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSC = 4;
+constexpr int kSCols = 8 * kSC + 8;                 // 40 output columns
+
+template <int CT>
+__global__ void __launch_bounds__(CT ? kSCols * (CT / 2) : 1024, CT ? 3 : 1)
+k_up8_bwd_strip(const float* __restrict__ prob, const float* __restrict__ score, const int* __restrict__ gt, const float* __restrict__ cls_out,
+                float up_cls, float threshold, const float* __restrict__ vpred, const float* __restrict__ lowres,
+                const float* __restrict__ bias_v, const float* __restrict__ centers,
+                const float* __restrict__ vtx_out, float up_vtx, float w_inside, float sigma2, int h, int w, int rb, int C_rt, int Cs, int Cv,
+                __nv_bfloat16* __restrict__ d_sc, __nv_bfloat16* __restrict__ d_vt, float* __restrict__ dbias_partial /*[ctas][4C]*/)
+{
+    // C even, 6 <= C <= 50: channel pairs; threads (column, 0..2) own the three vertex channels; kSCols * C / 2 threads
+    const int C = CT ? CT : C_rt;
+    const int CP = C / 2, No = 4 * C, VC = 3 * C, NT = kSCols * CP;
+    const int H = 8 * h, W = 8 * w;
+    const int c_lo = blockIdx.x * kSC, c_hi = min(c_lo + kSC, w);
+    const int m_lo = blockIdx.y * rb, m_hi = min(m_lo + rb, h);
+    const int n = blockIdx.z;
+    const float s_cls = up_cls / (cls_out[1] + 1e-10f), s_vtx = up_vtx / (vtx_out[1] + 1e-10f);
+    const size_t img = (size_t)n * H * W;
+    extern __shared__ float sm[];
+    float* v_s = sm;                                 // [kSCols][C]       finished vertical sums of the score channels
+    float* vacc = v_s + kSCols * C;                  // [2][kSCols][VC]   running vertical sums of the vertex channels
+    float* bs = vacc + 2 * kSCols * VC;              // [kSCols][C]       bias-gradient sums (score), per column
+    float* bv = bs + kSCols * C;                     // [kSCols][VC]      bias-gradient sums (vertex), per column
+    const int t = threadIdx.x, col = t / CP, j = t - col * CP;
+    for (int i = t; i < 2 * kSCols * VC; i += NT) vacc[i] = 0.f;
+    for (int i = t; i < kSCols * VC; i += NT) bv[i] = 0.f;
+    __syncthreads();
+    const int x = 8 * c_lo - 4 + col;
+    const bool xin = x >= 0 && x < W && x < 8 * c_hi + 4;
+    const bool own_x = x >= 8 * c_lo && x < 8 * c_hi;
+    float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int slot_lo = 0;                                 // vacc half of the OLDER low-resolution row (taps 8..15)
+    const float2* prob2 = reinterpret_cast<const float2*>(prob);
+    const float2* score2 = reinterpret_cast<const float2*>(score);
+    const int y_end = 8 * (m_hi - 1) + 11;
+    for (int y = 8 * m_lo - 4; y <= y_end; y++) {
+        const int kh = (y + 4) & 7;                  // tap of the newer row m_new = (y + 4) >> 3; the older row m_new - 1 sees tap kh + 8
+        if (xin && y >= 0 && y < H) {
+            const float w_hi = deconv_w(kh, 16), w_lo = deconv_w(kh + 8, 16);
+            const bool own = own_x && y >= 8 * m_lo && y < 8 * m_hi;
+            const size_t p = img + (size_t)y * W + x;
+            const int g = __ldg(gt + p);
+            if (g >= 0 && g < C) {
+                const float pg = __ldg(prob + p * C + g);
+                if (g > 0 || pg < threshold) {
+                    const float2 sv = __ldg(score2 + p * CP + j), pv = __ldg(prob2 + p * CP + j);
+                    const float d0 = sv.x > 0.f ? s_cls * (pv.x - (2 * j == g ? 1.f : 0.f)) : 0.f;
+                    const float d1 = sv.y > 0.f ? s_cls * (pv.y - (2 * j + 1 == g ? 1.f : 0.f)) : 0.f;
+                    lo0 = fmaf(w_lo, d0, lo0); lo1 = fmaf(w_lo, d1, lo1);
+                    hi0 = fmaf(w_hi, d0, hi0); hi1 = fmaf(w_hi, d1, hi1);
+                    if (own) { b0 += d0; b1 += d1; }
+                }
+                if (g > 0 && j < 3) {
+                    const float* cen = centers + ((size_t)n * C + g) * 3;
+                    const float z = cen[2];
+                    if (z > 0.f) {
+                        float tg;
+                        if (j == 2) tg = (float)log((double)z);
+                        else {
+                            const double dx = (double)cen[0] - (double)x, dy = (double)cen[1] - (double)y;
+                            const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+                            tg = (float)((j == 0 ? dx : dy) / nrm);
+                        }
+                        // vpred == NULL: the value is formed from the low-resolution head tensor (bit-identical, heads_common.cuh)
+                        const float pv = vpred ? __ldg(vpred + p * VC + 3 * g + j)
+                                               : up8_value(lowres, n, h, w, No, C + 3 * g + j, y, x, __ldg(bias_v + 3 * g + j));
+                        const float diff = w_inside * (pv - tg);
+                        const float ad = fabsf(diff);
+                        const float dt = ad < 1.f / sigma2 ? diff * sigma2 : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+                        const float d = s_vtx * w_inside * dt;
+                        float* a_lo = vacc + ((size_t)slot_lo * kSCols + col) * VC + 3 * g + j;
+                        float* a_hi = vacc + ((size_t)(slot_lo ^ 1) * kSCols + col) * VC + 3 * g + j;
+                        *a_lo = fmaf(w_lo, d, *a_lo);
+                        *a_hi = fmaf(w_hi, d, *a_hi);
+                        if (own) bv[col * VC + 3 * g + j] += d;
+                    }
+                }
+            }
+        }
+        if (kh == 7) {
+            // the older row m_old = ((y + 4) >> 3) - 1 has seen its last tap (15)
+            const int m_old = ((y + 4) >> 3) - 1;
+            if (m_old >= m_lo) {                      // block-uniform (m_old < m_hi by the loop bounds)
+                v_s[col * C + 2 * j] = lo0; v_s[col * C + 2 * j + 1] = lo1;
+                __syncthreads();
+                const float* va = vacc + (size_t)slot_lo * kSCols * VC;
+                for (int item = t; item < (c_hi - c_lo) * (Cs + Cv); item += NT) {
+                    const int ml = item / (Cs + Cv), ch = item - ml * (Cs + Cv);
+                    const size_t cell = ((size_t)n * h + m_old) * w + c_lo + ml;
+                    float acc = 0.f;
+                    if (ch < Cs) {
+                        if (ch < C) {
+#pragma unroll
+                            for (int kx = 0; kx < 16; kx++) acc = fmaf(deconv_w(kx, 16), v_s[(8 * ml + kx) * C + ch], acc);
+                        }
+                        d_sc[cell * Cs + ch] = __float2bfloat16_rn(acc);
+                    } else {
+                        const int c2 = ch - Cs;
+                        if (c2 < VC) {
+#pragma unroll
+                            for (int kx = 0; kx < 16; kx++) acc = fmaf(deconv_w(kx, 16), va[(8 * ml + kx) * VC + c2], acc);
+                        }
+                        d_vt[cell * Cv + c2] = __float2bfloat16_rn(acc);
+                    }
+                }
+                __syncthreads();
+            }
+            for (int i = t; i < kSCols * VC; i += NT) vacc[(size_t)slot_lo * kSCols * VC + i] = 0.f;
+            __syncthreads();
+            lo0 = hi0; lo1 = hi1; hi0 = 0.f; hi1 = 0.f;
+            slot_lo ^= 1;
+        }
+    }
+    bs[col * C + 2 * j] = b0; bs[col * C + 2 * j + 1] = b1;
+    __syncthreads();
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    for (int ch = t; ch < No; ch += NT) {
+        float acc = 0.f;
+        if (ch < C) { for (int q = 0; q < kSCols; q++) acc += bs[q * C + ch]; }
+        else { for (int q = 0; q < kSCols; q++) acc += bv[q * VC + ch - C]; }
+        dbias_partial[cta * No + ch] = acc;
+    }
 }
 
 // out[i] = scale * sum_k partial[k][i] (+ decay * p[i]); block = 32 columns x 8 row groups, groups combined in fixed order
@@ -385,16 +554,16 @@ static int ew_blocks(size_t total) { return (int)std::min<size_t>((total + 255) 
 
 extern "C" int pcnn_add_up2_bf16(const void* a4, const void* a5, int B, int h, int w, int C, void* out, void* stream)
 {
-    PCNN_REQUIRE(a4 && a5 && out && h % 2 == 0 && w % 2 == 0, "add_up2: bad arguments");
-    k_add_up2<<<ew_blocks((size_t)B * h * w * C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a4, (const __nv_bfloat16*)a5, B, h, w, C,
+    PCNN_REQUIRE(a4 && a5 && out && h % 2 == 0 && w % 2 == 0 && C % 8 == 0, "add_up2: bad arguments (even h, w; C %% 8 == 0)");
+    k_add_up2<<<ew_blocks((size_t)B * h * w * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a4, (const __nv_bfloat16*)a5, B, h, w, C,
                                                                                 (__nv_bfloat16*)out);
     return check_launch("add_up2");
 }
 
 extern "C" int pcnn_up2_bwd_bf16(const void* dadd, const void* y5, int B, int h, int w, int C, void* d5, void* stream)
 {
-    PCNN_REQUIRE(dadd && d5 && h % 2 == 0 && w % 2 == 0, "up2_bwd: bad arguments");
-    k_up2_bwd<<<ew_blocks((size_t)B * (h / 2) * (w / 2) * C), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dadd, (const __nv_bfloat16*)y5, B, h,
+    PCNN_REQUIRE(dadd && d5 && h % 2 == 0 && w % 2 == 0 && C % 8 == 0, "up2_bwd: bad arguments (even h, w; C %% 8 == 0)");
+    k_up2_bwd<<<ew_blocks((size_t)B * (h / 2) * (w / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dadd, (const __nv_bfloat16*)y5, B, h,
                                                                                             w, C, (__nv_bfloat16*)d5);
     return check_launch("up2_bwd");
 }
@@ -408,18 +577,60 @@ extern "C" int pcnn_pack_lowres(const void* sc, int Cs, const void* vt, int Cv, 
 }
 
 // d bias_score [C] and d bias_vertex [3C] come back in dbias [4C]; workspace: B * h * ceil(w / 16) * 4C floats
+// vertex_pred == NULL: the labelled pixels' vertex values come from `lowres` [B,h,w,4C] + bias_vertex [3C] (C = 22 strip kernel only)
+extern "C" int pcnn_up8_heads_bwd_ex(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
+                                     float threshold, const float* vertex_pred, const float* lowres, const float* bias_vertex, const float* centers,
+                                     const float* vertex_loss_out, float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C,
+                                     int Cs, int Cv, void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes,
+                                     void* stream);
+
 extern "C" int pcnn_up8_heads_bwd(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
                                   float threshold, const float* vertex_pred, const float* centers, const float* vertex_loss_out,
                                   float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C, int Cs, int Cv,
                                   void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes, void* stream)
 {
-    PCNN_REQUIRE(prob && score && gt && cls_loss_out && vertex_pred && centers && vertex_loss_out && d_sc_bf16 && d_vt_bf16 && dbias && workspace,
+    PCNN_REQUIRE(vertex_pred, "up8_heads_bwd: NULL tensor pointer");
+    return pcnn_up8_heads_bwd_ex(prob, score, gt, cls_loss_out, upstream_cls, threshold, vertex_pred, nullptr, nullptr, centers, vertex_loss_out,
+                                 upstream_vertex, w_inside, sigma, B, h, w, C, Cs, Cv, d_sc_bf16, d_vt_bf16, dbias, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pcnn_up8_heads_bwd_ex(const float* prob, const float* score, const int32_t* gt, const float* cls_loss_out, float upstream_cls,
+                                     float threshold, const float* vertex_pred, const float* lowres, const float* bias_vertex, const float* centers,
+                                     const float* vertex_loss_out, float upstream_vertex, float w_inside, float sigma, int B, int h, int w, int C,
+                                     int Cs, int Cv, void* d_sc_bf16, void* d_vt_bf16, float* dbias, void* workspace, size_t workspace_bytes,
+                                     void* stream)
+{
+    PCNN_REQUIRE(prob && score && gt && cls_loss_out && (vertex_pred || (lowres && bias_vertex)) && centers && vertex_loss_out && d_sc_bf16 &&
+                     d_vt_bf16 && dbias && workspace,
                  "up8_heads_bwd: NULL tensor pointer");
     PCNN_REQUIRE(Cs >= C && Cv >= 3 * C && h <= 65535 && B <= 65535, "up8_heads_bwd: bad shape");
     const int chunks = (w + kUbCells - 1) / kUbCells;
     const size_t need = sizeof(float) * (size_t)B * h * chunks * 4 * C;
-    PCNN_REQUIRE(workspace_bytes >= need, "up8_heads_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool strip_on = getenv("PCNN_UP8_BWD_STRIP") == nullptr || atoi(getenv("PCNN_UP8_BWD_STRIP")) != 0;
+    if (C % 2 == 0 && C >= 6 && C <= 50 && strip_on) {
+        // coalesced strip kernel (see k_up8_bwd_strip); partial bias sums: one row of 4C floats per CTA
+        const int rb = 16, bands = (h + rb - 1) / rb, strips = (w + kSC - 1) / kSC;
+        const size_t need2 = sizeof(float) * (size_t)B * strips * bands * 4 * C;
+        PCNN_REQUIRE(workspace_bytes >= need2, "up8_heads_bwd: workspace too small (%zu < %zu)", workspace_bytes, need2);
+        PCNN_REQUIRE(bands <= 65535, "up8_heads_bwd: bad shape");
+        const size_t smem2 = sizeof(float) * (size_t)kSCols * 11 * C;
+        const dim3 grid2(strips, bands, B);
+        if (C == 22)
+            k_up8_bwd_strip<22><<<grid2, kSCols * 11, smem2, st>>>(prob, score, gt, cls_loss_out, upstream_cls, threshold, vertex_pred, lowres, bias_vertex,
+                                                                  centers, vertex_loss_out, upstream_vertex, w_inside, sigma * sigma, h, w, rb, C, Cs, Cv,
+                                                                  (__nv_bfloat16*)d_sc_bf16, (__nv_bfloat16*)d_vt_bf16, (float*)workspace);
+        else {
+            PCNN_SMEM_OPTIN(k_up8_bwd_strip<0>, 100 * 1024, "up8_bwd_strip<0>");
+            k_up8_bwd_strip<0><<<grid2, kSCols * (C / 2), smem2, st>>>(prob, score, gt, cls_loss_out, upstream_cls, threshold, vertex_pred, lowres,
+                                                                      bias_vertex, centers, vertex_loss_out, upstream_vertex, w_inside, sigma * sigma, h, w,
+                                                                      rb, C, Cs, Cv, (__nv_bfloat16*)d_sc_bf16, (__nv_bfloat16*)d_vt_bf16,
+                                                                      (float*)workspace);
+        }
+        k_sum_partials<<<(4 * C + 31) / 32, 256, 0, st>>>((const float*)workspace, B * strips * bands, 4 * C, 1.f, nullptr, 0.f, dbias);
+        return check_launch("up8_heads_bwd");
+    }
+    PCNN_REQUIRE(vertex_pred, "up8_heads_bwd: the low-resolution vertex source needs the strip kernel (C even, 6..50)");
     dim3 grid(h, B, chunks);
     const size_t smem = sizeof(float) * ((size_t)kUbCols * 4 * C + 4 * C);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads_bwd: too many classes for the shared-memory column buffer (C = %d)", C);

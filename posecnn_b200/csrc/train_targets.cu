@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "heads_common.cuh"
 
 namespace pcnn {
 
@@ -336,19 +337,30 @@ k_pack_pose_meta(const float* __restrict__ poses /*[B,I,12]*/, const int* __rest
 }
 
 __global__ void __launch_bounds__(kLossThreads)
-k_vertex_loss_fused(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW,
+k_vertex_loss_fused(const float* __restrict__ pred, const float* __restrict__ lowres, const float* __restrict__ bias_v,
+                    const int* __restrict__ label, const float* __restrict__ centers, unsigned npix, int HW,
                     int W, int C, float w_inside, float sigma2, double* __restrict__ partial, unsigned* __restrict__ ticket,
                     float* __restrict__ out)
 {
+    // pred == NULL: the labelled pixels' three vertex values are formed on demand from the 1/8-resolution head tensor with
+    // k_up8_heads' own operation sequence (heads_common.cuh) — bit-identical to reading the dense vertex_pred
     __shared__ double sh[2 * kLossThreads / 32];
     double s = 0, sw = 0;
     for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
         int cls;
         float t[3], d;
         if (!pixel_targets(label, centers, pix, HW, W, C, cls, t)) continue;
-        const float* pp = pred + (size_t)pix * 3 * C + 3 * cls;
+        if (pred) {
+            const float* pp = pred + (size_t)pix * 3 * C + 3 * cls;
 #pragma unroll
-        for (int k = 0; k < 3; k++) s += (double)sl1_term(__ldg(pp + k), t[k], w_inside, sigma2, d);
+            for (int k = 0; k < 3; k++) s += (double)sl1_term(__ldg(pp + k), t[k], w_inside, sigma2, d);
+        } else {
+            const int b = pix / HW, pp = pix - b * HW, y = pp / W, x = pp - y * W;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                s += (double)sl1_term(up8_value(lowres, b, (HW / W) >> 3, W >> 3, 4 * C, C + 3 * cls + k, y, x, __ldg(bias_v + 3 * cls + k)), t[k],
+                                      w_inside, sigma2, d);
+        }
         sw += 3.0 * (double)w_inside;
     }
     block_reduce2(s, sw, sh);
@@ -396,14 +408,33 @@ extern "C" int pcnn_vertex_loss_fused_fwd(const float* pred, const int32_t* labe
     unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
     const unsigned npix = (unsigned)B * H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    k_vertex_loss_fused<<<kLossBlocks, kLossThreads, 0, st>>>(pred, label, centers, npix, H * W, W, C, w_inside, sigma * sigma, partial, ticket,
-                                                               loss_out);
+    k_vertex_loss_fused<<<kLossBlocks, kLossThreads, 0, st>>>(pred, nullptr, nullptr, label, centers, npix, H * W, W, C, w_inside, sigma * sigma,
+                                                               partial, ticket, loss_out);
     if (grad_pred) {
         cudaMemsetAsync(grad_pred, 0, sizeof(float) * (size_t)npix * 3 * C, st);
         k_vertex_loss_fused_grad<<<kNumSMs * 16, 256, 0, st>>>(pred, label, centers, npix, H * W, W, C, w_inside, sigma * sigma, loss_out,
                                                                 upstream, grad_pred);
     }
     return check_launch("vertex_loss_fused");
+}
+
+// the same loss with the vertex head given as the 1/8-resolution head tensor `lowres` [B,H/8,W/8,4C] (channels C.. = vertex) + the
+// vertex_pred bias [3C]: no dense vertex_pred tensor is needed anywhere in the training step
+extern "C" int pcnn_vertex_loss_fused_lowres_fwd(const float* lowres, const float* bias_vertex, const int32_t* label, const float* centers, int B,
+                                                 int H, int W, int C, float w_inside, float sigma, float* loss_out, void* workspace,
+                                                 size_t workspace_bytes, void* stream)
+{
+    PCNN_REQUIRE(lowres && bias_vertex && label && centers && loss_out && workspace, "vertex_loss_fused_lowres: NULL tensor pointer");
+    PCNN_REQUIRE(sigma > 0.f && B >= 1 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0 && C >= 1, "vertex_loss_fused_lowres: bad arguments");
+    PCNN_REQUIRE((unsigned long long)B * H * W < 0xffffffffULL, "vertex_loss_fused_lowres: too many pixels");
+    size_t need = 0;
+    pcnn_train_loss_workspace_bytes(&need);
+    PCNN_REQUIRE(workspace_bytes >= need, "vertex_loss_fused_lowres: workspace too small (%zu < %zu)", workspace_bytes, need);
+    double* partial = (double*)workspace;
+    unsigned* ticket = (unsigned*)(partial + 2 * kLossBlocks);
+    k_vertex_loss_fused<<<kLossBlocks, kLossThreads, 0, (cudaStream_t)stream>>>(nullptr, lowres, bias_vertex, label, centers, (unsigned)B * H * W, H * W,
+                                                                                 W, C, w_inside, sigma * sigma, partial, ticket, loss_out);
+    return check_launch("vertex_loss_fused_lowres");
 }
 
 extern "C" int pcnn_train_loss_workspace_bytes(size_t* bytes)

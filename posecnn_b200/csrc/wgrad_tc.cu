@@ -47,6 +47,12 @@ struct WgParams {
     int n_tile, n_tiles, m_tiles;          // N tile (64 / 128 / 256), Cin / n_tile, ceil(Cout / 128)
     int f16;                               // operands are FP16 (the fully connected head) instead of BF16
     int tg, tap_groups;                    // taps per work item (Cin <= 128: several taps share one MMA as extra N blocks), ceil(taps / tg)
+    // splits == 1 (the fully connected layers: more (Cout, Cin) tiles than two waves of CTAs): the epilogue writes the finished
+    // gradient dW[co][tap * Cin + ci] = scale * acc (+ decay * w) itself; no partial buffer, no k_wgrad_finish pass
+    int direct;
+    float scale, decay;
+    const float* w;
+    float* dW;
 };
 
 // MN-major, 128-byte-swizzled operand: K rows of 128 B (64 channels), 8-row groups 1024 B apart (SBO), 64-channel
@@ -177,12 +183,26 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
             if (co < p.Cout) {
                 const int j = g >> 1;                                   // B block of these 32 columns
                 const int tap = tap0 + j / cb, ci = n0 + 64 * (j % cb) + 32 * (g & 1);
-                float* dst = partial + (((size_t)split * p.taps + tap) * p.Cout + co) * p.Cin + ci;
+                if (p.direct) {
+                    const size_t o = ((size_t)co * p.taps + tap) * p.Cin + ci;
 #pragma unroll
-                for (int q = 0; q < 8; q++)
-                    *reinterpret_cast<float4*>(dst + q * 4) =
-                        make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                    __uint_as_float(r[4 * q + 3]));
+                    for (int q = 0; q < 8; q++) {
+                        float4 v = make_float4(__uint_as_float(r[4 * q]) * p.scale, __uint_as_float(r[4 * q + 1]) * p.scale,
+                                               __uint_as_float(r[4 * q + 2]) * p.scale, __uint_as_float(r[4 * q + 3]) * p.scale);
+                        if (p.w) {
+                            const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + o) + q);
+                            v.x = fmaf(p.decay, wv.x, v.x); v.y = fmaf(p.decay, wv.y, v.y); v.z = fmaf(p.decay, wv.z, v.z); v.w = fmaf(p.decay, wv.w, v.w);
+                        }
+                        *reinterpret_cast<float4*>(p.dW + o + q * 4) = v;
+                    }
+                } else {
+                    float* dst = partial + (((size_t)split * p.taps + tap) * p.Cout + co) * p.Cin + ci;
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        *reinterpret_cast<float4*>(dst + q * 4) =
+                            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                        __uint_as_float(r[4 * q + 3]));
+                }
             }
         }
         tc_fence_before();
@@ -427,6 +447,7 @@ static int plan(int B, int H, int W, int Cin, int Cout, int ksize, WgParams* p)
     if (want > p->ktiles) want = p->ktiles;
     p->ktiles_per_split = (p->ktiles + want - 1) / want;
     p->splits = (p->ktiles + p->ktiles_per_split - 1) / p->ktiles_per_split;
+    p->direct = 0; p->scale = 1.f; p->decay = 0.f; p->w = nullptr; p->dW = nullptr;
     return PCNN_OK;
 }
 
@@ -484,9 +505,10 @@ static int wgrad_impl(const void* x_bf16, const void* dz_bf16, int B, int H, int
     cudaStream_t st = (cudaStream_t)stream;
     const long long items = (long long)p.splits * p.tap_groups * p.n_tiles * p.m_tiles;
     PCNN_REQUIRE(items < 0x7fffffffLL, "conv_wgrad: too many work items");
+    if (p.splits == 1) { p.direct = 1; p.scale = scale; p.decay = decay; p.w = w_f32; p.dW = dW; }
     k_wgrad_tc<<<(unsigned)items, kWgThreads, kWgSmem, st>>>(mx, mz, (float*)workspace, p);
     rc = check_launch("wgrad_tc");
-    if (rc) return rc;
+    if (rc || p.direct) return rc;
     const size_t n4 = (size_t)p.taps * Cout * Cin / 4;
     int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)kNumSMs * 8);
     k_wgrad_finish<<<blocks, 256, 0, st>>>((const float*)workspace, p.splits, p.taps, Cout, Cin, scale, w_f32, decay, dW);

@@ -164,26 +164,28 @@ class Trainer:
         lowres = torch.empty((B, h, w, 4 * C), dtype=torch.float32, device=data.device)
         check(lib().pcnn_pack_lowres(ptr(lr_s), 64, ptr(lr_v), 128, B, h, w, C, ptr(lowres), stream()))
         label = torch.empty((B, H, W), dtype=torch.int32, device=data.device)
-        vertex = torch.empty((B, H, W, 3 * C), dtype=torch.float32, device=data.device)
         prob = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device)
         score = torch.empty((B, H, W, C), dtype=torch.float32, device=data.device)
-        check(lib().pcnn_up8_heads(ptr(lowres), ptr(M["score/b"]), ptr(M["vertex_pred/b"]), B, h, w, C, ptr(label), ptr(vertex), ptr(prob),
+        # The dense vertex_pred [B,H,W,3C] (81 MB / frame) is never written: its only consumers — the vertex loss, its gradient and the
+        # Hough sampler — read three values per labelled / sampled pixel and form them on demand from `lowres` with k_up8_heads' own
+        # operation sequence (heads_common.cuh: bit-identical).  dense_vertex_pred(A) materialises it for inspection.
+        check(lib().pcnn_up8_heads(ptr(lowres), ptr(M["score/b"]), ptr(M["vertex_pred/b"]), B, h, w, C, ptr(label), ptr(None), ptr(prob),
                                    ptr(score), stream()))
-        A.update(s4=s4, s5=s5, v4=v4, v5=v5, add_s=add_s, add_v=add_v, label_2d=label, vertex_pred=vertex, prob_normalized=prob, score=score)
+        A.update(s4=s4, s5=s5, v4=v4, v5=v5, add_s=add_s, add_v=add_v, label_2d=label, lowres=lowres, prob_normalized=prob, score=score)
         # losses on the dense heads (fused kernels; the masks / targets are never materialised)
         ws = train_ops._workspace(data.device)
         cls_out = torch.empty((2,), dtype=torch.float32, device=data.device)
         check(lib().pcnn_loss_cls_hard_raw_fwd(ptr(score), ptr(prob), ptr(gt_label_2d), B, H, W, C, f32(net.threshold_label), ptr(cls_out), ptr(ws),
                                                ctypes.c_size_t(ws.numel()), stream()))
         vtx_out = torch.empty((2,), dtype=torch.float32, device=data.device)
-        check(lib().pcnn_vertex_loss_fused_fwd(ptr(vertex), ptr(gt_label_2d), ptr(centers), B, H, W, C, f32(self.w_inside), f32(1.0), ptr(vtx_out),
-                                               f32(1.0), ptr(None), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+        check(lib().pcnn_vertex_loss_fused_lowres_fwd(ptr(lowres), ptr(M["vertex_pred/b"]), ptr(gt_label_2d), ptr(centers), B, H, W, C,
+                                                      f32(self.w_inside), f32(1.0), ptr(vtx_out), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
         A.update(cls_out=cls_out, vtx_out=vtx_out)
         # Hough voting in train mode (9 jittered ROIs per maximum, quaternion targets from the gt poses)
         Bg = B if batch_global is None else int(batch_global)
         box, pose, target, weight, domain, num_rois, status = hough_voting_gpu_op.hough_voting_gpu_capacity(
-            label, vertex, extents, meta_data, gt_poses, 1, net.vote_threshold, net.vote_percentage, net.skip_pixels, batch_global=Bg,
-            batch_offset=batch_offset)
+            label, None, extents, meta_data, gt_poses, 1, net.vote_threshold, net.vote_percentage, net.skip_pixels, lowres=lowres,
+            bias_vertex=M["vertex_pred/b"], batch_global=Bg, batch_offset=batch_offset)
         # the op's output has a data-dependent number of rows (9 per kept maximum): one host read, like the reference's
         # copy_num_rois (hough_voting_gpu_op.cu.cc:591-594); Averagedistance then normalises by the true row count
         host = torch.cat([num_rois, status[:2]]).tolist()
@@ -204,6 +206,17 @@ class Trainer:
         A.update(rois=rl, num_rois=num_rois, a5=a5, a4=a4, pool=pool, fc6=f6, fc7=f7, poses_tanh=tanh, poses_weight=wt, poses_target=tw,
                  pose_diff=pose_diff, loss_pose_raw=loss_pose, rows=rows, data=data)
         return A
+
+    def dense_vertex_pred(self, A):
+        """The dense vertex_pred [B,H,W,3C] of a forward pass (the training step itself never materialises it)."""
+        lowres = A["lowres"]
+        B, h, w, _ = lowres.shape
+        C, M = self.C, self.master
+        label = torch.empty((B, 8 * h, 8 * w), dtype=torch.int32, device=lowres.device)
+        vertex = torch.empty((B, 8 * h, 8 * w, 3 * C), dtype=torch.float32, device=lowres.device)
+        check(lib().pcnn_up8_heads(ptr(lowres), ptr(M["score/b"]), ptr(M["vertex_pred/b"]), B, h, w, C, ptr(label), ptr(vertex), ptr(None),
+                                   ptr(None), stream()))
+        return vertex
 
     # ------------------------------------------------------------------ gradient plumbing
     def _emit(self, grads, name, g):
@@ -291,11 +304,11 @@ class Trainer:
         d_sc = torch.empty((B, h, w, 64), dtype=torch.bfloat16, device=dev)
         d_vt = torch.empty((B, h, w, 128), dtype=torch.bfloat16, device=dev)
         dbias = torch.empty((4 * C,), dtype=torch.float32, device=dev)
-        ws = workspace("up8_bwd", 4 * B * h * ((w + 15) // 16) * 4 * C, dev)
-        check(lib().pcnn_up8_heads_bwd(ptr(A["prob_normalized"]), ptr(A["score"]), ptr(gt_label_2d), ptr(A["cls_out"]), f32(1.0),
-                                       f32(net.threshold_label), ptr(A["vertex_pred"]), ptr(centers), ptr(A["vtx_out"]), f32(self.vertex_w),
-                                       f32(self.w_inside), f32(1.0), B, h, w, C, 64, 128, ptr(d_sc), ptr(d_vt), ptr(dbias), ptr(ws),
-                                       ctypes.c_size_t(ws.numel()), stream()))
+        ws = workspace("up8_bwd", 4 * B * max(h * ((w + 15) // 16), ((w + 3) // 4) * ((h + 15) // 16)) * 4 * C, dev)
+        check(lib().pcnn_up8_heads_bwd_ex(ptr(A["prob_normalized"]), ptr(A["score"]), ptr(gt_label_2d), ptr(A["cls_out"]), f32(1.0),
+                                          f32(net.threshold_label), ptr(None), ptr(A["lowres"]), ptr(M["vertex_pred/b"]), ptr(centers),
+                                          ptr(A["vtx_out"]), f32(self.vertex_w), f32(self.w_inside), f32(1.0), B, h, w, C, 64, 128, ptr(d_sc),
+                                          ptr(d_vt), ptr(dbias), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
         self._emit(grads, "score/b", dbias[:C].contiguous())
         self._emit(grads, "vertex_pred/b", dbias[C:].contiguous())
         self._emit(grads, "score/w", bw.conv_wgrad(A["add_s"], d_sc, 1))

@@ -150,3 +150,115 @@ def test_fc_dgrad_wgrad_and_pose_chain(cuda):
     dpre = torch.empty((N, 128), dtype=torch.float16, device=cuda)
     check(lib().pcnn_pose_chain_bwd(ptr(gup), ptr(th.detach().contiguous()), ptr(wt), N, D, f32(1.0), ptr(dpre), 128, stream()))
     assert rel_l2(dpre[:, :D].float(), pre.grad) < 2e-3 and float(dpre[:, D:].float().abs().max()) == 0.0
+
+
+def _up8_problem(cuda, B, h, w, C, seed):
+    """A low-resolution head tensor, its dense up-sampling (pcnn_up8_heads), ground-truth labels with ignore / background /
+    foreground pixels, centres with one listed and one unlisted class."""
+    import ctypes
+    from posecnn_b200._lib import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(seed)
+    H, W = 8 * h, 8 * w
+    lowres = (torch.randn(B, h, w, 4 * C, generator=g) * 0.7).to(cuda)
+    bs, bv = (torch.randn(C, generator=g) * 0.1).to(cuda), (torch.randn(3 * C, generator=g) * 0.1).to(cuda)
+    label = torch.empty((B, H, W), dtype=torch.int32, device=cuda)
+    vertex = torch.empty((B, H, W, 3 * C), device=cuda)
+    prob, score = torch.empty((B, H, W, C), device=cuda), torch.empty((B, H, W, C), device=cuda)
+    check(lib().pcnn_up8_heads(ptr(lowres), ptr(bs), ptr(bv), B, h, w, C, ptr(label), ptr(vertex), ptr(prob), ptr(score), stream()))
+    gt = torch.randint(-1, C, (B, H, W), generator=g).to(torch.int32)
+    gt[:, : H // 3] = 0                                                      # a background region (Hardlabel: selected only if uncertain)
+    gt[:, H // 3: H // 2, : W // 2] = 3                                      # a coherent object
+    gt = gt.to(cuda)
+    centers = torch.zeros(B, C, 3)
+    for c in range(1, C):
+        if c != 2:                                                           # class 2 is labelled but not listed (z = 0)
+            centers[:, c] = torch.tensor([W * 0.3 + 3 * c, H * 0.6 - 2 * c, 0.5 + 0.05 * c])
+    return dict(lowres=lowres, bs=bs, bv=bv, vertex=vertex, prob=prob, score=score, gt=gt, centers=centers.to(cuda), B=B, h=h, w=w, C=C)
+
+
+def _up8_bwd(P, dense, thr=0.7, up_cls=1.0, up_vtx=2.0, w_in=10.0, sigma=1.0, count=937.0, sumw=411.0):
+    import ctypes
+    from posecnn_b200._lib import check, f32, lib, ptr, stream
+    B, h, w, C = P["B"], P["h"], P["w"], P["C"]
+    dev = P["lowres"].device
+    d_sc = torch.full((B, h, w, 64), 7.0, dtype=torch.bfloat16, device=dev)
+    d_vt = torch.full((B, h, w, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    dbias = torch.empty((4 * C,), device=dev)
+    cls_out, vtx_out = torch.tensor([0.5, count], device=dev), torch.tensor([0.25, sumw], device=dev)
+    ws = torch.empty(4 * B * max(h * ((w + 15) // 16), ((w + 3) // 4) * ((h + 15) // 16)) * 4 * C, dtype=torch.uint8, device=dev)
+    check(lib().pcnn_up8_heads_bwd_ex(ptr(P["prob"]), ptr(P["score"]), ptr(P["gt"]), ptr(cls_out), f32(up_cls), f32(thr),
+                                      ptr(P["vertex"] if dense else None), ptr(None if dense else P["lowres"]), ptr(None if dense else P["bv"]),
+                                      ptr(P["centers"]), ptr(vtx_out), f32(up_vtx), f32(w_in), f32(sigma), B, h, w, C, 64, 128, ptr(d_sc), ptr(d_vt),
+                                      ptr(dbias), ptr(ws), ctypes.c_size_t(ws.numel()), stream()))
+    return d_sc, d_vt, dbias
+
+
+@pytest.mark.parametrize("C,h,w", [(22, 8, 12), (6, 18, 10), (22, 60, 80)])
+def test_up8_heads_backward_against_torch(cuda, C, h, w):
+    """Gradient of the Hardlabel cross entropy and of the vertex smooth-L1 w.r.t. the low-resolution head tensor
+    (k_up8_bwd_strip) against the formulas of lib/fcn/train.py:455-465, 564-573 written in torch and the adjoint of the fixed
+    bilinear x8 transposed convolution (network.py:141-157, 207-222) = a stride-8 depthwise convolution with the same filter.
+    The low-resolution vertex source (no dense vertex_pred) gives bit-identical results."""
+    B = 2
+    P = _up8_problem(cuda, B, h, w, C, seed=C + h)
+    thr, up_cls, up_vtx, w_in, sigma, count, sumw = 0.7, 1.0, 2.0, 10.0, 1.0, 937.0, 411.0
+    d_sc, d_vt, dbias = _up8_bwd(P, dense=True)
+    e_sc, e_vt, ebias = _up8_bwd(P, dense=False)
+    print("dense vs low-resolution vertex source: max |d_vt diff| %.3e, max |dbias diff| %.3e" % (
+        (d_vt.float() - e_vt.float()).abs().max().item(), (dbias - ebias).abs().max().item()))
+    assert torch.equal(d_sc, e_sc)
+    if C == 22:                                   # the compile-time-stride kernels share one operation sequence (heads_common.cuh)
+        assert torch.equal(d_vt, e_vt) and torch.equal(dbias, ebias)
+    H, W = 8 * h, 8 * w
+    gt = P["gt"].long()
+    prob, score, vertex = P["prob"], P["score"], P["vertex"]
+    valid = gt >= 0
+    g0 = gt.clamp(min=0)
+    pg = prob.gather(3, g0[..., None])[..., 0]
+    sel = valid & ((gt > 0) | (pg < thr))
+    onehot = F.one_hot(g0, C).float()
+    d_up_s = (up_cls / (count + 1e-10)) * sel[..., None] * (prob - onehot) * (score > 0)
+    cen = P["centers"]
+    ys, xs = torch.meshgrid(torch.arange(H, device=cuda), torch.arange(W, device=cuda), indexing="ij")
+    cpix = cen[torch.arange(B, device=cuda)[:, None, None], g0]                                  # [B,H,W,3]
+    listed = (gt > 0) & (cpix[..., 2] > 0)
+    dx, dy = cpix[..., 0].double() - xs, cpix[..., 1].double() - ys
+    nrm = (dx * dx + dy * dy).sqrt() + 1e-10
+    tg = torch.stack([(dx / nrm).float(), (dy / nrm).float(), cpix[..., 2].clamp(min=1e-30).double().log().float()], -1)
+    own = vertex.view(B, H, W, C, 3).gather(3, g0[..., None, None].expand(B, H, W, 1, 3))[..., 0, :]
+    diff = w_in * (own - tg)
+    dt = torch.where(diff.abs() < 1.0 / sigma ** 2, diff * sigma ** 2, diff.sign())
+    d_own = (up_vtx / (sumw + 1e-10)) * w_in * dt * listed[..., None]
+    d_up_v = torch.zeros(B, H, W, C, 3, device=cuda).scatter_(3, g0[..., None, None].expand(B, H, W, 1, 3), d_own[..., None, :]).view(B, H, W, 3 * C)
+    d_up = torch.cat([d_up_s, d_up_v], 3).permute(0, 3, 1, 2).contiguous()
+    k1 = torch.tensor([1.0 - abs(i / 8.0 - 0.9375) for i in range(16)], device=cuda)
+    filt = (k1[:, None] * k1[None, :])[None, None].expand(4 * C, 1, 16, 16).contiguous()
+    want = F.conv2d(d_up, filt, stride=8, padding=4, groups=4 * C).permute(0, 2, 3, 1)             # [B,h,w,4C]
+    assert rel_l2(d_sc[..., :C].float(), want[..., :C]) < 4e-3                                     # bf16 output rounding
+    for vt_, b_ in ((d_vt, dbias), (e_vt, ebias)):
+        assert rel_l2(vt_[..., :3 * C].float(), want[..., C:]) < 4e-3
+        assert (vt_[..., 3 * C:].float() == 0).all()                                               # GEMM padding channels
+        assert torch.allclose(b_, d_up.sum((0, 2, 3)), rtol=2e-4, atol=1e-7)
+    assert (d_sc[..., C:].float() == 0).all()
+
+
+def test_add_up2_and_adjoint(cuda):
+    """add = a4 + up2(a5) (fixed bilinear conv2d_transpose 4x4 / 2, vgg16_convs.py:134-138) and the adjoint with the ReLU mask."""
+    from posecnn_b200._lib import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(5)
+    B, h, w, C = 2, 12, 16, 64
+    a4 = torch.randn(B, h, w, C, generator=g).to(torch.bfloat16).to(cuda)
+    a5 = torch.randn(B, h // 2, w // 2, C, generator=g).to(torch.bfloat16).to(cuda)
+    out = torch.empty_like(a4)
+    check(lib().pcnn_add_up2_bf16(ptr(a4), ptr(a5), B, h, w, C, ptr(out), stream()))
+    k1 = torch.tensor([1.0 - abs(i / 2.0 - 0.75) for i in range(4)], device=cuda)
+    filt = (k1[:, None] * k1[None, :])[None, None].expand(C, 1, 4, 4).contiguous()
+    up = F.conv_transpose2d(a5.float().permute(0, 3, 1, 2), filt, stride=2, padding=1, groups=C).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), a4.float() + up) < 3e-3
+    dadd = torch.randn(B, h, w, C, generator=g).to(torch.bfloat16).to(cuda)
+    d5 = torch.empty_like(a5)
+    check(lib().pcnn_up2_bwd_bf16(ptr(dadd), ptr(a5), B, h, w, C, ptr(d5), stream()))
+    want = F.conv2d(dadd.float().permute(0, 3, 1, 2), filt, stride=2, padding=1, groups=C).permute(0, 2, 3, 1) * (a5.float() > 0)
+    assert rel_l2(d5.float(), want) < 3e-3
+    check(lib().pcnn_up2_bwd_bf16(ptr(dadd), ptr(None), B, h, w, C, ptr(d5), stream()))
+    assert rel_l2(d5.float(), F.conv2d(dadd.float().permute(0, 3, 1, 2), filt, stride=2, padding=1, groups=C).permute(0, 2, 3, 1)) < 3e-3

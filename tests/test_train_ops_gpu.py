@@ -222,3 +222,31 @@ def test_pack_pose_meta_matches_data_layer_restatement(cuda):
             np.testing.assert_allclose(qa, qb, atol=2e-6)
         np.testing.assert_allclose(got[:n, 10:], wb[:, 10:], atol=0)
         np.testing.assert_allclose(meta.cpu().numpy().reshape(B, 48), wm, rtol=1e-6, atol=1e-9)
+
+
+def test_vertex_loss_from_lowres_equals_dense(cuda):
+    """pcnn_vertex_loss_fused_lowres_fwd (vertex values formed on demand from the 1/8-resolution head tensor) == the fused loss on
+    the dense vertex_pred produced by pcnn_up8_heads from the same tensor: the training step needs no dense vertex_pred."""
+    import ctypes
+    from posecnn_b200 import synth, train_ops
+    from posecnn_b200._lib import check, f32, lib, ptr, stream
+    B, H, W, C = 2, 96, 128, 22
+    sc = synth.make_scene(batch=B, height=H, width=W, num_classes=C, seed=5, objects_per_image=4, min_pixels=100)
+    g = torch.Generator().manual_seed(9)
+    lowres = (torch.randn(B, H // 8, W // 8, 4 * C, generator=g) * 0.5).to(cuda)
+    bs, bv = torch.zeros(C, device=cuda), (torch.randn(3 * C, generator=g) * 0.1).to(cuda)
+    label = torch.empty((B, H, W), dtype=torch.int32, device=cuda)
+    vertex = torch.empty((B, H, W, 3 * C), device=cuda)
+    check(lib().pcnn_up8_heads(ptr(lowres), ptr(bs), ptr(bv), B, H // 8, W // 8, C, ptr(label), ptr(vertex), ptr(None), ptr(None), stream()))
+    centers = np.zeros((B, C, 3), np.float32)
+    for (b, cls, cx, cy, z) in sc["centers"]:
+        centers[b, cls] = (cx, cy, z)
+    lab, cen = T(sc["label"], cuda), T(centers, cuda)
+    for sigma in (1.0, 2.0):
+        l0, w0 = train_ops.vertex_loss_from_centers(vertex, lab, cen, 10.0, sigma, want_grad=False)
+        out = torch.empty((2,), device=cuda)
+        ws = train_ops._workspace(cuda)
+        check(lib().pcnn_vertex_loss_fused_lowres_fwd(ptr(lowres), ptr(bv), ptr(lab), ptr(cen), B, H, W, C, f32(10.0), f32(sigma), ptr(out), ptr(ws),
+                                                      ctypes.c_size_t(ws.numel()), stream()))
+        assert float(w0.item()) == float(out[1].item()) > 0
+        assert float(l0.item()) == float(out[0].item())
