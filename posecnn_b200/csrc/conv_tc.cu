@@ -862,34 +862,40 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
 k_im2col_c3(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W, float m0, float m1, float m2)
 {
-    // grid = (ceil(W / 32), H, B): a CTA builds 32 pixels x 64 K-values of one image row.  The 3 x 34 x 3 input patch
-    // (mean subtracted, zero outside the image = SAME padding) is staged in shared memory; thread (x, j) then packs
-    // the 8 K-values k = 8j .. 8j+7 (K order tap*3 + c) into one 16-byte store.
-    __shared__ float patch[3][34 * 3];
-    const int y = blockIdx.y, n = blockIdx.z, x0 = blockIdx.x * 32, t = threadIdx.x;
+    // grid = (ceil(W / 128), H, B): a CTA builds 128 pixels x 64 K-values of one image row in four 32-pixel passes (614 k tiny
+    // CTAs at batch 64 were launch-bound).  The 3 x 130 x 3 input patch (mean subtracted, zero outside the image = SAME padding)
+    // is staged in shared memory once; thread (x, j) then packs the 8 K-values k = 8j .. 8j+7 (K order tap*3 + c) into one 16-byte store.
+    constexpr int kSeg = 128;
+    __shared__ float patch[3][(kSeg + 2) * 3];
+    const int y = blockIdx.y, n = blockIdx.z, x0 = blockIdx.x * kSeg, t = threadIdx.x;
     const TIn* img = in + (size_t)n * H * W * 3;
-    for (int i = t; i < 3 * 34 * 3; i += 256) {
-        const int r = i / 102, rem = i - r * 102, px = rem / 3, c = rem - px * 3;
+    constexpr int kRow = (kSeg + 2) * 3;
+    for (int i = t; i < 3 * kRow; i += 256) {
+        const int r = i / kRow, rem = i - r * kRow, px = rem / 3, c = rem - px * 3;
         const int yy = y + r - 1, xx = x0 + px - 1;
         float v = 0.f;
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = (float)img[(yy * W + xx) * 3 + c] - (c == 0 ? m0 : (c == 1 ? m1 : m2));
         patch[r][rem] = v;
     }
     __syncthreads();
-    const int xl = t >> 3, j = t & 7, x = x0 + xl;
-    if (x >= W) return;
-    __align__(16) __nv_bfloat16 v[8];
+    const int j = t & 7;
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int k = j * 8 + e;  // tap = k / 3 (dy = tap / 3, dx = tap % 3), c = k % 3 -> patch[dy][(xl + dx) * 3 + c]
-        float val = 0.f;
-        if (k < 27) {
-            const int dy = k / 9, rem = k - dy * 9;  // rem = dx * 3 + c
-            val = patch[dy][xl * 3 + rem];
+    for (int pass = 0; pass < kSeg / 32; pass++) {
+        const int xl = pass * 32 + (t >> 3), x = x0 + xl;
+        if (x >= W) break;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int k = j * 8 + e;  // tap = k / 3 (dy = tap / 3, dx = tap % 3), c = k % 3 -> patch[dy][(xl + dx) * 3 + c]
+            float val = 0.f;
+            if (k < 27) {
+                const int dy = k / 9, rem = k - dy * 9;  // rem = dx * 3 + c
+                val = patch[dy][xl * 3 + rem];
+            }
+            v[e] = __float2bfloat16_rn(val);
         }
-        v[e] = __float2bfloat16_rn(val);
+        *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * 64 + j * 8) = *reinterpret_cast<const uint4*>(v);
     }
-    *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * 64 + j * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
 // 2x2 / stride 2 max pool, NHWC bf16 (Network.max_pool, network.py:303-310; H, W even here)
@@ -1088,7 +1094,7 @@ extern "C" int pcnn_im2col_c3(const void* in, int in_is_u8, const float* mean3_h
     float m0 = 0.f, m1 = 0.f, m2 = 0.f;
     if (mean3_host) { m0 = mean3_host[0]; m1 = mean3_host[1]; m2 = mean3_host[2]; }
     PCNN_REQUIRE(H <= 65535 && B <= 65535, "im2col: image too tall for the launch grid");
-    dim3 grid((W + 31) / 32, H, B);
+    dim3 grid((W + 127) / 128, H, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (in_is_u8)
         k_im2col_c3<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)in, (__nv_bfloat16*)out_bf16, H, W, m0, m1, m2);

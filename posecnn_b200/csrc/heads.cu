@@ -239,6 +239,7 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     const int s_lo = max(c_lo - 1, 0), s_hi = min(c_hi + 1, w);                 // source cells incl. halo
     float2* rowi = reinterpret_cast<float2*>(smem_f) - (size_t)s_lo * N2;       // [s_lo, s_hi) x N2, indexed by absolute cell
     float* sc = smem_f + (size_t)(seg_cells + 2) * No - (size_t)8 * c_lo * C;   // [8 seg_cells][C], indexed by absolute x
+    float* stat = smem_f + (size_t)(seg_cells + 2) * No + (size_t)8 * seg_cells * C;   // [8 seg_cells][2]: softmax max / sum of a pixel
     const int y = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
     // conv2d_transpose 16x16 / stride 8, SAME (pad 4): out[o] = sum_i in[i] * W[o - 8i + 4]
     const int my = y >> 3, ty = y & 7;
@@ -330,11 +331,25 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
             }
         label[rowbase + x] = bi;
         if (prob) {
+            // softmax statistics of the pixel; the normalised row is written by the cooperative pass below
             const float* s = sc + x * C;
             float sum = 0.f;
             for (int c = 0; c < C; c++) sum += expf(s[c] - best);
-            float* pr = prob + (rowbase + x) * C;
-            for (int c = 0; c < C; c++) pr[c] = expf(s[c] - best) / sum;
+            stat[2 * (x - 8 * c_lo)] = best;
+            stat[2 * (x - 8 * c_lo) + 1] = sum;
+        }
+    }
+    if (prob) {
+        // prob_normalized = exp(s - max) / sum (network.py:474-488), thread = (pixel, class) in memory order: the segment's
+        // 8 (c_hi - c_lo) * C floats are one contiguous run of the output row -> coalesced stores (thread = pixel wrote C floats
+        // 88 B apart: 22 store instructions of 32 scattered sectors each)
+        __syncthreads();
+        const int nel = 8 * (c_hi - c_lo) * C;
+        const float* s = sc + (size_t)8 * c_lo * C;
+        float* pr = prob + (rowbase + 8 * (size_t)c_lo) * C;
+        for (int i = t; i < nel; i += 256) {
+            const int xl = i / C;
+            pr[i] = expf(s[i] - stat[2 * xl]) / stat[2 * xl + 1];
         }
     }
 }
@@ -489,7 +504,7 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
         }
     }
     int seg_cells = w <= 20 ? w : 20;  // 160 output pixels per CTA
-    size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C);
+    size_t smem = sizeof(float) * ((size_t)(seg_cells + 2) * 4 * C + (size_t)8 * seg_cells * C + (size_t)16 * seg_cells);
     PCNN_REQUIRE(smem <= 200 * 1024, "up8_heads: segment does not fit shared memory (C = %d)", C);
     dim3 grid(8 * h, B, (w + seg_cells - 1) / seg_cells);
     PCNN_SMEM_OPTIN(k_up8_heads<0>, 200 * 1024, "up8_heads<0>");

@@ -74,12 +74,22 @@ struct Layout {
         work_ctr, cand_key, cand_val, cand_n, cand_data, votes, total;
 };
 
-static int band_rows(int W)
+static int band_rows(int B, int H, int W, int C)
 {
     // difference array of one band: R rows x (W + 3) ints; 16 rows = 41 KB at W = 640, so four
     // CTAs (32 warps) fit per SM and the work items are fine grained enough to balance
     int R = 16;
     while (R > 1 && (size_t)R * (W + 3) * 4 > 48 * 1024) R >>= 1;
+    // Small batches (an image shard of a multi-GPU batch, configs[1]): an item's cost is its class's samples x R rows and the kernel
+    // cannot finish before its heaviest item, so with few items (B x C x H / R < ~16 per resident CTA) the bands are halved:
+    // measured (profiles/r02_hough_band_rows_sweep.txt) batch 1: 0.087 -> 0.071 ms, batch 4: 0.194 -> 0.136 ms on the 8(d) scenes,
+    // 0.39 -> 0.24 ms on the network's maps; 4 and 2 rows bring nothing more.  Results do not depend on R (tests run B = 1, 2, 4
+    // and 32).  PCNN_HOUGH_BAND_ROWS overrides (power of two).
+    static const int forced = getenv("PCNN_HOUGH_BAND_ROWS") ? atoi(getenv("PCNN_HOUGH_BAND_ROWS")) : 0;
+    if (forced >= 1 && forced <= R && (forced & (forced - 1)) == 0) return forced;
+    static const int min_rows = getenv("PCNN_HOUGH_BAND_MIN") ? atoi(getenv("PCNN_HOUGH_BAND_MIN")) : 8;
+    const long long want = 16LL * 4 * kNumSMs;
+    while (R > min_rows && (long long)B * C * ((H + R - 1) / R) < want) R >>= 1;
     return R;
 }
 
@@ -88,7 +98,7 @@ static Layout make_layout(int B, int H, int W, int C, int skip, bool want_votes,
     Layout L;
     size_t HW = (size_t)H * W;
     L.nchunks = (int)((HW + kChunk - 1) / kChunk);
-    L.R = band_rows(W);
+    L.R = band_rows(B, H, W, C);
     L.nbands = (H + L.R - 1) / L.R;
     L.samp_cap = (int)((HW + skip - 1) / skip) + C;
     L.cand_cap = threshold_mode ? kCandCapThr : C;

@@ -272,7 +272,7 @@ constexpr int kSC = 4;
 constexpr int kSCols = 8 * kSC + 8;                 // 40 output columns
 
 template <int CT>
-__global__ void __launch_bounds__(CT ? kSCols * (CT / 2) : 1024, CT ? 3 : 1)
+__global__ void __launch_bounds__(CT ? kSCols * (CT / 2) : 1024, CT ? 2 : 1)
 k_up8_bwd_strip(const float* __restrict__ prob, const float* __restrict__ score, const int* __restrict__ gt, const float* __restrict__ cls_out,
                 float up_cls, float threshold, const float* __restrict__ vpred, const float* __restrict__ lowres,
                 const float* __restrict__ bias_v, const float* __restrict__ centers,
@@ -293,7 +293,12 @@ k_up8_bwd_strip(const float* __restrict__ prob, const float* __restrict__ score,
     float* vacc = v_s + kSCols * C;                  // [2][kSCols][VC]   running vertical sums of the vertex channels
     float* bs = vacc + 2 * kSCols * VC;              // [kSCols][C]       bias-gradient sums (score), per column
     float* bv = bs + kSCols * C;                     // [kSCols][VC]      bias-gradient sums (vertex), per column
+    float* logz = bv + kSCols * VC;                  // [C]               log of the listed centre depth of each class of this image
     const int t = threadIdx.x, col = t / CP, j = t - col * CP;
+    for (int i = t; i < C; i += NT) {
+        const float z = centers[((size_t)n * C + i) * 3 + 2];
+        logz[i] = z > 0.f ? (float)log((double)z) : 0.f;
+    }
     for (int i = t; i < 2 * kSCols * VC; i += NT) vacc[i] = 0.f;
     for (int i = t; i < kSCols * VC; i += NT) bv[i] = 0.f;
     __syncthreads();
@@ -302,59 +307,109 @@ k_up8_bwd_strip(const float* __restrict__ prob, const float* __restrict__ score,
     const bool own_x = x >= 8 * c_lo && x < 8 * c_hi;
     float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f, b0 = 0.f, b1 = 0.f;
     int slot_lo = 0;                                 // vacc half of the OLDER low-resolution row (taps 8..15)
-    const float2* prob2 = reinterpret_cast<const float2*>(prob);
-    const float2* score2 = reinterpret_cast<const float2*>(score);
     const int y_end = 8 * (m_hi - 1) + 11;
-    for (int y = 8 * m_lo - 4; y <= y_end; y++) {
+    // Three-stage software pipeline over the rows (the loads of a row depend on its label: label -> selected? -> score / prob pair):
+    // row y + 2: label + background probability in flight; row y + 1: label known, its score / prob pair in flight; row y: consumed.
+    // Hardlabel selects a background pixel only if prob[.., 0] < threshold and every foreground pixel, so the one probability the
+    // selection needs is channel 0 — independent of the label's value, loaded together with it.
+    // Addressing: per-thread base pointers at (image n, row 0, column x) and ONE 32-bit pixel-row offset `ro` advanced by W per row
+    // (the first version recomputed `img + y W + x` in 64 bits for every load: 135 instructions per row, 9 % of them loads or math).
+    const int y_first = max(8 * m_lo - 4, 0);        // rows above the image contribute nothing and complete no low-resolution row
+    const int y_last = min(y_end, H - 1);            // last row with pixels; the loop runs to y_end for the final hand-over
+    const int xs = xin ? x : 0;                      // a thread outside the strip / image never loads (labels stay -1)
+    const int* gt_c = gt + img + xs;
+    const float* pr0_c = prob + (img + xs) * C;
+    const float2* sc2_c = reinterpret_cast<const float2*>(score) + (img + xs) * CP + j;
+    const float2* pr2_c = reinterpret_cast<const float2*>(prob) + (img + xs) * CP + j;
+    const int j2 = 2 * j;
+    const int own_lo = 8 * m_lo, own_hi = 8 * m_hi;
+    // vertex role (threads t < kSCols): column xB, labels prefetched two rows ahead
+    const int xB = 8 * c_lo - 4 + t;
+    const bool xinB = t < kSCols && xB >= 0 && xB < W && xB < 8 * c_hi + 4;
+    const bool ownB_x = xB >= 8 * c_lo && xB < 8 * c_hi;
+    const int* gtB_c = gt + img + (xinB ? xB : 0);
+    // running pointers, advanced by one image row per iteration: labels / background probability two rows ahead, score / prob pair one
+    // row ahead (pointer bumps keep the loop body free of 64-bit index multiplications)
+    const size_t r0 = (size_t)y_first * W;
+    const int* gp2 = gt_c + r0 + 2 * (size_t)W;
+    const float* qp2 = pr0_c + (r0 + 2 * (size_t)W) * C;
+    const float2* sp1 = sc2_c + (r0 + W) * CP;
+    const float2* pp1 = pr2_c + (r0 + W) * CP;
+    const int* gpB2 = gtB_c + r0 + 2 * (size_t)W;
+    const size_t stepQ = (size_t)W * C, stepS = (size_t)W * CP;
+    int gB0 = -1, gB1 = -1;
+    if (xinB) {
+        if (y_first <= y_last) gB0 = __ldg(gtB_c + r0);
+        if (y_first + 1 <= y_last) gB1 = __ldg(gtB_c + r0 + W);
+    }
+    int g0 = -1, g1 = -1, g2;
+    float q0 = 0.f, q1 = 0.f, q2;
+    float2 sv0 = make_float2(0.f, 0.f), pv0 = sv0, sv1 = sv0, pv1 = sv0;
+    if (xin) {
+        if (y_first <= y_last) { g0 = __ldg(gt_c + r0); q0 = __ldg(pr0_c + r0 * C); }
+        if (y_first + 1 <= y_last) { g1 = __ldg(gt_c + r0 + W); q1 = __ldg(pr0_c + (r0 + W) * C); }
+    }
+    bool s0 = (unsigned)g0 < (unsigned)C && (g0 > 0 || q0 < threshold);
+    if (s0) { sv0 = __ldg(sc2_c + r0 * CP); pv0 = __ldg(pr2_c + r0 * CP); }
+    for (int y = y_first; y <= y_end; y++) {
         const int kh = (y + 4) & 7;                  // tap of the newer row m_new = (y + 4) >> 3; the older row m_new - 1 sees tap kh + 8
-        if (xin && y >= 0 && y < H) {
-            const float w_hi = deconv_w(kh, 16), w_lo = deconv_w(kh + 8, 16);
-            const bool own = own_x && y >= 8 * m_lo && y < 8 * m_hi;
-            const size_t p = img + (size_t)y * W + x;
-            const int g = __ldg(gt + p);
-            if (g >= 0 && g < C) {
-                const float pg = __ldg(prob + p * C + g);
-                if (g > 0 || pg < threshold) {
-                    const float2 sv = __ldg(score2 + p * CP + j), pv = __ldg(prob2 + p * CP + j);
-                    const float d0 = sv.x > 0.f ? s_cls * (pv.x - (2 * j == g ? 1.f : 0.f)) : 0.f;
-                    const float d1 = sv.y > 0.f ? s_cls * (pv.y - (2 * j + 1 == g ? 1.f : 0.f)) : 0.f;
-                    lo0 = fmaf(w_lo, d0, lo0); lo1 = fmaf(w_lo, d1, lo1);
-                    hi0 = fmaf(w_hi, d0, hi0); hi1 = fmaf(w_hi, d1, hi1);
-                    if (own) { b0 += d0; b1 += d1; }
-                }
-                if (g > 0 && j < 3) {
-                    const float* cen = centers + ((size_t)n * C + g) * 3;
-                    const float z = cen[2];
-                    if (z > 0.f) {
-                        float tg;
-                        if (j == 2) tg = (float)log((double)z);
-                        else {
-                            const double dx = (double)cen[0] - (double)x, dy = (double)cen[1] - (double)y;
-                            const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
-                            tg = (float)((j == 0 ? dx : dy) / nrm);
-                        }
+        const float w_hi = 1.f - fabsf((float)kh * 0.125f - 0.9375f), w_lo = 1.f - fabsf((float)(kh + 8) * 0.125f - 0.9375f);   // deconv_w(., 16)
+        g2 = -1; q2 = 0.f;
+        if (xin && y + 2 <= y_last) { g2 = __ldg(gp2); q2 = __ldg(qp2); }
+        const bool s1 = (unsigned)g1 < (unsigned)C && (g1 > 0 || q1 < threshold);
+        if (s1) { sv1 = __ldg(sp1); pv1 = __ldg(pp1); }
+        gp2 += W; qp2 += stepQ; sp1 += stepS; pp1 += stepS;
+        if (s0) {
+            const float d0 = sv0.x > 0.f ? s_cls * (pv0.x - (j2 == g0 ? 1.f : 0.f)) : 0.f;
+            const float d1 = sv0.y > 0.f ? s_cls * (pv0.y - (j2 + 1 == g0 ? 1.f : 0.f)) : 0.f;
+            lo0 = fmaf(w_lo, d0, lo0); lo1 = fmaf(w_lo, d1, lo1);
+            hi0 = fmaf(w_hi, d0, hi0); hi1 = fmaf(w_hi, d1, hi1);
+            if (own_x && y >= own_lo && y < own_hi) { b0 += d0; b1 += d1; }
+        }
+        // ---- vertex role: thread t < kSCols owns output column t of the strip (all three vertex channels of the pixel's class).
+        // The target direction needs a double sqrt and two double divisions per labelled pixel (the reference forms it in float64,
+        // minibatch.py:582-594); keeping that on 40 densely packed lanes instead of three lanes of every column costs 1/7 of the
+        // double-precision issue slots (the (column, k) mapping made the whole kernel FP64-bound: 3.2 ms at batch 64).
+        if (t < kSCols) {
+            const int gB = gB0;
+            if (gB > 0 && gB < C) {
+                const float* cen = centers + ((size_t)n * C + gB) * 3;
+                if (cen[2] > 0.f) {
+                    const bool ownB = ownB_x && y >= own_lo && y < own_hi;
+                    const double dx = (double)cen[0] - (double)xB, dy = (double)cen[1] - (double)y;
+                    const double nrm = sqrt(dx * dx + dy * dy) + 1e-10;
+                    const float tg[3] = {(float)(dx / nrm), (float)(dy / nrm), logz[gB]};
+                    const size_t pB = img + (size_t)y * W + xB;
+                    float* a_lo = vacc + ((size_t)slot_lo * kSCols + t) * VC + 3 * gB;
+                    float* a_hi = vacc + ((size_t)(slot_lo ^ 1) * kSCols + t) * VC + 3 * gB;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
                         // vpred == NULL: the value is formed from the low-resolution head tensor (bit-identical, heads_common.cuh)
-                        const float pv = vpred ? __ldg(vpred + p * VC + 3 * g + j)
-                                               : up8_value(lowres, n, h, w, No, C + 3 * g + j, y, x, __ldg(bias_v + 3 * g + j));
-                        const float diff = w_inside * (pv - tg);
+                        const float pv = vpred ? __ldg(vpred + pB * VC + 3 * gB + k)
+                                               : up8_value(lowres, n, h, w, No, C + 3 * gB + k, y, xB, __ldg(bias_v + 3 * gB + k));
+                        const float diff = w_inside * (pv - tg[k]);
                         const float ad = fabsf(diff);
                         const float dt = ad < 1.f / sigma2 ? diff * sigma2 : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
                         const float d = s_vtx * w_inside * dt;
-                        float* a_lo = vacc + ((size_t)slot_lo * kSCols + col) * VC + 3 * g + j;
-                        float* a_hi = vacc + ((size_t)(slot_lo ^ 1) * kSCols + col) * VC + 3 * g + j;
-                        *a_lo = fmaf(w_lo, d, *a_lo);
-                        *a_hi = fmaf(w_hi, d, *a_hi);
-                        if (own) bv[col * VC + 3 * g + j] += d;
+                        a_lo[k] = fmaf(w_lo, d, a_lo[k]);
+                        a_hi[k] = fmaf(w_hi, d, a_hi[k]);
+                        if (ownB) bv[t * VC + 3 * gB + k] += d;
                     }
                 }
             }
+            gB0 = gB1;
+            gB1 = (xinB && y + 2 <= y_last) ? __ldg(gpB2) : -1;
+            gpB2 += W;
         }
+        g0 = g1; q0 = q1; s0 = s1; sv0 = sv1; pv0 = pv1; g1 = g2; q1 = q2;
         if (kh == 7) {
             // the older row m_old = ((y + 4) >> 3) - 1 has seen its last tap (15)
             const int m_old = ((y + 4) >> 3) - 1;
             if (m_old >= m_lo) {                      // block-uniform (m_old < m_hi by the loop bounds)
                 v_s[col * C + 2 * j] = lo0; v_s[col * C + 2 * j + 1] = lo1;
-                __syncthreads();
+            }
+            __syncthreads();                          // every thread's updates of vacc for this row are done (also when the row is discarded)
+            if (m_old >= m_lo) {
                 const float* va = vacc + (size_t)slot_lo * kSCols * VC;
                 for (int item = t; item < (c_hi - c_lo) * (Cs + Cv); item += NT) {
                     const int ml = item / (Cs + Cv), ch = item - ml * (Cs + Cv);
@@ -614,7 +669,7 @@ extern "C" int pcnn_up8_heads_bwd_ex(const float* prob, const float* score, cons
         const size_t need2 = sizeof(float) * (size_t)B * strips * bands * 4 * C;
         PCNN_REQUIRE(workspace_bytes >= need2, "up8_heads_bwd: workspace too small (%zu < %zu)", workspace_bytes, need2);
         PCNN_REQUIRE(bands <= 65535, "up8_heads_bwd: bad shape");
-        const size_t smem2 = sizeof(float) * (size_t)kSCols * 11 * C;
+        const size_t smem2 = sizeof(float) * ((size_t)kSCols * 11 * C + C);
         const dim3 grid2(strips, bands, B);
         if (C == 22)
             k_up8_bwd_strip<22><<<grid2, kSCols * 11, smem2, st>>>(prob, score, gt, cls_loss_out, upstream_cls, threshold, vertex_pred, lowres, bias_vertex,

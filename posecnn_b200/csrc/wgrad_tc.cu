@@ -50,6 +50,12 @@ struct WgParams {
     // splits == 1 (the fully connected layers: more (Cout, Cin) tiles than two waves of CTAs): the epilogue writes the finished
     // gradient dW[co][tap * Cin + ci] = scale * acc (+ decay * w) itself; no partial buffer, no k_wgrad_finish pass
     int direct;
+    // Cout = Cin = 64, 3x3 (conv1_2): a 64-channel dZ block fills only half of the M = 128 operand.  The upper half then holds the SAME
+    // dZ channels one image row further down (box origin h0 + 1): D[64 + co, tap (2, s)] = sum_p dZ[p + (1, 0), co] X[p + (1, s - 1)] =
+    // dW[tap (1, s)] — the item with the B blocks of taps (2, 0..2) (N = 192) produces taps (2, s) in lanes 0..63 and taps (1, s) in
+    // lanes 64..127; a second item does taps (0, s) with a zero upper half.  Two N = 192 items instead of three (N = 256, 256, 64):
+    // 192 instead of 340 MMA clocks per 16 pixels.  The tile grid starts at image row -1 so that row 0 of dZ meets the upper half.
+    int pair64, h_org;
     float scale, decay;
     const float* w;
     float* dW;
@@ -94,7 +100,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
     const int k_lo = split * p.ktiles_per_split, k_hi = min(k_lo + p.ktiles_per_split, p.ktiles);
     const int nk = k_hi - k_lo;
     const int m0 = mt * 128, n0 = nt * p.n_tile;
-    const int tap0 = tgi * p.tg, ntaps = min(p.tg, p.taps - tap0);
+    const int tap0 = p.pair64 ? (tgi == 0 ? 6 : 0) : tgi * p.tg, ntaps = min(p.tg, p.taps - tap0);
+    const bool up_shift = p.pair64 && tgi == 0;         // upper A block = dZ one row down (see WgParams::pair64)
     const int cb = p.n_tile / 64;                       // 64-channel B blocks per tap
     const int nb = ntaps * cb;                          // B blocks per stage (<= 4): block j = (tap0 + j / cb, channels n0 + 64 (j % cb))
     const int n_item = nb * 64;                         // UMMA N of this item
@@ -111,7 +118,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
         mbar_init(tfull, 1);
         fence_barrier_init();
     }
-    if (!a2) {
+    if (!a2 && !up_shift) {
         // Cout tile of 64 channels only: the upper half of the M = 128 operand stays zero for the whole kernel
         for (int s = 0; s < kWgStages; s++)
             for (int i = threadIdx.x; i < kWgBlk / 16; i += kWgThreads)
@@ -128,7 +135,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (uint32_t)((a2 ? 2 : 1) + nb) * kWgBlk;
+            const uint32_t tx = (uint32_t)((a2 || up_shift ? 2 : 1) + nb) * kWgBlk;
             int bdx[kWgMaxNB], bdy[kWgMaxNB], bch[kWgMaxNB];       // per B block: tap offset and channel origin (loop invariant)
 #pragma unroll
             for (int j = 0; j < kWgMaxNB; j++) {
@@ -140,12 +147,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
                 const int tw = kt % p.tiles_w; kt /= p.tiles_w;
                 const int th = kt % p.tiles_h;
                 const int img = kt / p.tiles_h;
-                const int w0 = tw * p.bw, h0 = th * p.bh;
+                const int w0 = tw * p.bw, h0 = th * p.bh + p.h_org;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = smem + stage * kWgStage;
                 mbar_arrive_expect_tx(&full[stage], tx);
                 tma_load_4d(st, &map_dz, &full[stage], m0, w0, h0, img);
                 if (a2) tma_load_4d(st + kWgBlk, &map_dz, &full[stage], m0 + 64, w0, h0, img);
+                else if (up_shift) tma_load_4d(st + kWgBlk, &map_dz, &full[stage], m0, w0, h0 + 1, img);
 #pragma unroll
                 for (int j = 0; j < kWgMaxNB; j++)
                     if (j < nb) tma_load_4d(st + (2 + j) * kWgBlk, &map_x, &full[stage], bch[j], w0 + bdx[j], h0 + bdy[j], img);
@@ -174,7 +182,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
         // epilogue: TMEM lane = output channel of the tile, columns = input channels of the tile
         mbar_wait(tfull, 0);
         tc_fence_after();
-        const int co = m0 + warp * 32 + lane;
+        const bool upper = up_shift && warp >= 2;           // lanes 64..127 of the paired item: the same channels, tap - 3
+        const int co = m0 + warp * 32 + lane - (upper ? 64 : 0);
         const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int g = 0; g < n_item / 32; g++) {
             uint32_t r[32];
@@ -182,7 +191,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap map_x /*[B,H,W,Cin] box {64,bw,bh
             tmem_ld_wait();
             if (co < p.Cout) {
                 const int j = g >> 1;                                   // B block of these 32 columns
-                const int tap = tap0 + j / cb, ci = n0 + 64 * (j % cb) + 32 * (g & 1);
+                const int tap = tap0 + j / cb - (upper ? 3 : 0), ci = n0 + 64 * (j % cb) + 32 * (g & 1);
                 if (p.direct) {
                     const size_t o = ((size_t)co * p.taps + tap) * p.Cin + ci;
 #pragma unroll
@@ -441,6 +450,12 @@ static int plan(int B, int H, int W, int Cin, int Cout, int ksize, WgParams* p)
     // Cin <= 128: N = Cin alone would issue small (N = 64 / 128) MMAs; several taps ride in one instruction as extra N blocks
     p->tg = (p->n_tiles == 1 && p->n_tile < 256 && p->taps > 1) ? 256 / p->n_tile : 1;
     p->tap_groups = (p->taps + p->tg - 1) / p->tg;
+    p->pair64 = 0; p->h_org = 0;
+    if (Cout == 64 && Cin == 64 && ksize == 3 && H > 1) {
+        p->pair64 = 1; p->h_org = -1; p->tg = 3; p->tap_groups = 2;
+        p->tiles_h = (H + 1 + p->bh - 1) / p->bh;
+        p->ktiles = B * p->tiles_h * p->tiles_w;
+    }
     const int base = p->tap_groups * p->n_tiles * p->m_tiles;
     int want = (2 * kNumSMs) / base;                     // just under two full waves of work items (no third, nearly empty wave)
     if (want < 1) want = 1;
