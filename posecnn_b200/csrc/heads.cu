@@ -362,8 +362,12 @@ k_up8_heads(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
 // pixel takes the arg-max (lowest index on ties).  Same operation sequence as k_up8_heads (heads_common.cuh): identical
 // labels.  CT = compile-time class count (even).
 // ---------------------------------------------------------------------------------------------
+// 512 threads: the kernel is latency-bound (shared-memory chains between two barriers per output row); with 77 KB of shared
+// memory per CTA only two CTAs fit an SM, so the warps have to come from the CTA itself
+constexpr int kLabelThreads = 512;
+
 template <int CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kLabelThreads)
 k_up8_label(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict__ bias_s /*[C]*/, int h, int w, int C_rt,
             int* __restrict__ label /*[B,8h,8w]*/)
 {
@@ -373,7 +377,7 @@ k_up8_label(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
     float2* rows = reinterpret_cast<float2*>(smem_f);              // [3][w][C2]: low-resolution rows my - 1, my, my + 1 (score channels)
     float* sc = smem_f + (size_t)3 * w * C;                        // [W][C] scores of one output row
     const int my = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
-    for (int i = t; i < 3 * w * C2; i += 256) {
+    for (int i = t; i < 3 * w * C2; i += kLabelThreads) {
         const int r = i / (w * C2), j = i - r * (w * C2);
         const int cell = j / C2, c2 = j - cell * C2;
         const int iy = min(max(my - 1 + r, 0), h - 1);             // clamped like k_up8_heads; out-of-range rows get weight 0
@@ -388,7 +392,7 @@ k_up8_label(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
         const float wy1 = (iy1 >= 0 && iy1 < h) ? deconv_w(y - 8 * iy1 + 4, 16) : 0.f;
         const float2* r0 = rows + (size_t)(iy0 - (my - 1)) * w * C2;     // staged slot of row iy0 (slot 0..2); clamping is
         const float2* r1 = rows + (size_t)(iy1 - (my - 1)) * w * C2;     // irrelevant where the weight is 0, identical otherwise
-        for (int i = t; i < w * C2; i += 256) {
+        for (int i = t; i < w * C2; i += kLabelThreads) {
             const int mx = i / C2, c2 = i - mx * C2;
             const float2 bb = make_float2(__ldg(bias_s + 2 * c2), __ldg(bias_s + 2 * c2 + 1));
             auto vb = [&](int cell) -> float2 {
@@ -409,7 +413,7 @@ k_up8_label(const float* __restrict__ lr /*[B,h,w,4C]*/, const float* __restrict
             }
         }
         __syncthreads();
-        for (int x = t; x < W; x += 256) {
+        for (int x = t; x < W; x += kLabelThreads) {
             const float2* s2 = reinterpret_cast<const float2*>(sc + (size_t)x * C);
             float best = s2[0].x;
             int bi = 0;
@@ -495,10 +499,10 @@ extern "C" int pcnn_up8_heads(const float* lowres, const float* bias_score, cons
             dim3 grid_l(h, B);
             if (C == 22) {
                 PCNN_SMEM_OPTIN(k_up8_label<22>, 200 * 1024, "up8_label<22>");
-                k_up8_label<22><<<grid_l, 256, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
+                k_up8_label<22><<<grid_l, kLabelThreads, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
             } else {
                 PCNN_SMEM_OPTIN(k_up8_label<0>, 200 * 1024, "up8_label<0>");
-                k_up8_label<0><<<grid_l, 256, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
+                k_up8_label<0><<<grid_l, kLabelThreads, smem_l, (cudaStream_t)stream>>>(lowres, bias_score, h, w, C, label);
             }
             return check_launch("up8_label");
         }
