@@ -38,6 +38,32 @@ def test_abi_argument_validation_without_gpu(native_lib):
     assert native_lib.pcnn_roi_pool_fwd(None, None, 1, 5, 1, 4, 4, 4, 7, 7, ctypes.c_float(1.0), 0, None, None, None) == -1
 
 
+def test_host_planning_without_gpu(native_lib):
+    """Host-side planning of the round-2 kernels (no CUDA call): Hough band height by batch size, weight-gradient work split incl. the
+    paired Cout = Cin = 64 case and the single-split (direct-epilogue) fully connected case, NULL / shape validation of the new entries."""
+    nbytes = ctypes.c_size_t(0)
+    ws = {}
+    for B in (1, 2, 4, 8, 16, 32, 64):
+        assert native_lib.pcnn_hough_vote_workspace_bytes(B, 480, 640, 22, 10, ctypes.c_float(-1.0), ctypes.byref(nbytes)) == 0
+        ws[B] = nbytes.value
+    assert all(ws[a] < ws[b] for a, b in zip((1, 2, 4, 8, 16, 32), (2, 4, 8, 16, 32, 64)))      # monotone in the batch size
+    # 8-row bands below ~16 items per resident CTA (B <= 8 at C = 22, H = 480), 16 rows above: the per-image band table doubles
+    assert ws[8] / 8 > ws[16] / 16
+    for (B, H, W, Cin, Cout, k) in [(16, 480, 640, 64, 64, 3), (2, 20, 36, 64, 64, 3), (16, 60, 80, 512, 512, 3), (1, 1, 117, 25088, 4096, 1),
+                                    (1, 1, 37, 1024, 256, 1), (4, 30, 40, 512, 64, 1)]:
+        assert native_lib.pcnn_conv_wgrad_workspace_bytes(B, H, W, Cin, Cout, k, ctypes.byref(nbytes)) == 0
+        per_split = 4 * k * k * Cin * Cout
+        assert nbytes.value >= per_split and nbytes.value % 256 == 0
+        splits = nbytes.value // per_split
+        assert 1 <= splits <= 2 * 148                                                              # at most two waves of work items
+    assert native_lib.pcnn_conv_wgrad_workspace_bytes(1, 8, 8, 48, 64, 3, ctypes.byref(nbytes)) == -1  # Cin % 64
+    f1 = ctypes.c_float(1.0)
+    assert native_lib.pcnn_up8_heads_bwd_ex(None, None, None, None, f1, f1, None, None, None, None, None, f1, f1, f1, 1, 8, 8, 22, 64, 128,
+                                            None, None, None, None, ctypes.c_size_t(0), None) == -1
+    assert native_lib.pcnn_vertex_loss_fused_lowres_fwd(None, None, None, None, 1, 64, 96, 22, ctypes.c_float(1.0), ctypes.c_float(1.0), None,
+                                                        None, ctypes.c_size_t(0), None) == -1
+
+
 def test_ops_refuse_cpu_tensors(native_lib):
     import torch
     from posecnn_b200.hard_label_layer import hard_label_op
