@@ -79,7 +79,10 @@ def test_end_to_end_label_flip_rate(net_and_out):
 
 def test_hough_roi_pose_head_composition(net_and_out):
     """rois / poses_init from the pipeline == oracle Hough on the pipeline's own label / vertex maps; poses_tanh ==
-    fp32 torch pose head on the pipeline's conv features and rois (bf16 GEMMs: abs 1e-2 on tanh outputs)."""
+    fp32 torch pose head on the pipeline's conv features and rois.  This is the composition check at a loose 2e-2 (a Kaiming-initialised
+    fc8 drives tanh into saturation, where small pre-activation differences flip nothing but are not comparable either); the stated
+    1e-3 on the quaternions (SURVEY 8(c)) is enforced by tests/test_fullsize_gpu.py::test_pose_head_480x640_against_fp32_head on
+    O(0.2) pre-activations, together with 1.5e-3 rel-L2 on the fc6 / fc7 / fc8 activations of the fp16 tensor-core head."""
     net, data, meta, ext, out = net_and_out
     want = oracle.hough_voting_gpu(to_np(out["label_2d"]), to_np(out["vertex_pred"]), to_np(ext), to_np(meta), None, 0, -1.0,
                                    0.02, 10)
